@@ -1,0 +1,848 @@
+// kt_api.cu -- the C ABI of include/kerrtrace.h: contexts, device-resident ray sets, launch orchestration.
+// Host code only (kernels live in kt_kernels.cu, compiled once per arithmetic mode).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "kt_types.h"
+#include "kt_kernels.h"
+
+using kt::KernelTable;
+using kt::LaunchCfg;
+using kt::PlaneFrame;
+using kt::PointSourceFrame;
+using kt::TraceParams;
+
+// ---------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define KT_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess) return fail(KT_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* kt_last_error(void) { return g_err; }
+extern "C" int kt_version(void) { return KT_VERSION; }
+
+// ---------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------
+struct kt_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;     // the stream work is issued on (own_stream or the caller's)
+    unsigned long long* d_queue = nullptr;
+    double* d_scratch = nullptr;       // small reduction buffer (histograms, counters)
+    size_t scratch_bytes = 0;
+    kt_ray* d_rays = nullptr;          // staging for the host-buffer entry points
+    size_t rays_bytes = 0;
+    double* h_pinned = nullptr;        // pinned bounce buffer for small results
+    size_t pinned_bytes = 0;
+    long long launches = 0;
+    int min_blocks = 0;
+};
+
+struct kt_rayset {
+    kt_ctx* ctx;
+    long long n;
+    kt_ray* d;
+};
+
+extern "C" int kt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+static int ctx_bind(kt_ctx* c)
+{
+    if (!c) return fail(KT_ERR_INVALID, "null context");
+    KT_CUDA(cudaSetDevice(c->device));
+    return KT_OK;
+}
+
+static int ensure_scratch(kt_ctx* c, size_t bytes)
+{
+    if (c->scratch_bytes >= bytes) return KT_OK;
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    c->d_scratch = nullptr;
+    c->scratch_bytes = 0;
+    if (cudaMalloc(&c->d_scratch, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(KT_ERR_NOMEM, "device allocation of %zu bytes failed", bytes);
+    }
+    c->scratch_bytes = bytes;
+    return KT_OK;
+}
+
+static int ensure_pinned(kt_ctx* c, size_t bytes)
+{
+    if (c->pinned_bytes >= bytes) return KT_OK;
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    c->h_pinned = nullptr;
+    c->pinned_bytes = 0;
+    if (cudaHostAlloc(&c->h_pinned, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(KT_ERR_NOMEM, "pinned allocation of %zu bytes failed", bytes);
+    }
+    c->pinned_bytes = bytes;
+    return KT_OK;
+}
+
+static int ensure_rays(kt_ctx* c, size_t bytes)
+{
+    if (c->rays_bytes >= bytes) return KT_OK;
+    if (c->d_rays) cudaFree(c->d_rays);
+    c->d_rays = nullptr;
+    c->rays_bytes = 0;
+    if (cudaMalloc(&c->d_rays, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(KT_ERR_NOMEM, "device allocation of %zu bytes failed", bytes);
+    }
+    c->rays_bytes = bytes;
+    return KT_OK;
+}
+
+extern "C" kt_ctx* kt_create(int device)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        fail(KT_ERR_CUDA, "no CUDA device available (%s): the kerrtrace engine has no CPU fallback",
+             e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) {
+        fail(KT_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+        return nullptr;
+    }
+    kt_ctx* c = new (std::nothrow) kt_ctx;
+    if (!c) return nullptr;
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&c->d_queue, sizeof(unsigned long long)) != cudaSuccess) {
+        fail(KT_ERR_CUDA, "context creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return nullptr;
+    }
+    c->sm_count = prop.multiProcessorCount;
+    c->stream = c->own_stream;
+    const char* mb = getenv("KT_MIN_BLOCKS");
+    c->min_blocks = mb ? atoi(mb) : 0;
+    if (ensure_scratch(c, 1 << 20) != KT_OK || ensure_pinned(c, 1 << 20) != KT_OK) {
+        kt_destroy(c);
+        return nullptr;
+    }
+    return c;
+}
+
+extern "C" void kt_destroy(kt_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->d_queue) cudaFree(c->d_queue);
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    if (c->d_rays) cudaFree(c->d_rays);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" int kt_set_stream(kt_ctx* c, void* s)
+{
+    if (!c) return fail(KT_ERR_INVALID, "null context");
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return KT_OK;
+}
+
+extern "C" int kt_synchronize(kt_ctx* c)
+{
+    if (int rc = ctx_bind(c)) return rc;
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    return KT_OK;
+}
+
+extern "C" int kt_sm_count(kt_ctx* c) { return c ? c->sm_count : 0; }
+extern "C" int64_t kt_kernel_launches(kt_ctx* c) { return c ? c->launches : 0; }
+extern "C" int kt_set_min_blocks(kt_ctx* c, int mb)
+{
+    if (!c) return fail(KT_ERR_INVALID, "null context");
+    c->min_blocks = mb;
+    return KT_OK;
+}
+
+extern "C" void* kt_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        fail(KT_ERR_NOMEM, "pinned allocation of %zu bytes failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void kt_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+static LaunchCfg cfg_of(kt_ctx* c)
+{
+    LaunchCfg cfg;
+    cfg.stream = c->stream;
+    cfg.sm_count = c->sm_count;
+    cfg.min_blocks = c->min_blocks;
+    return cfg;
+}
+
+static const KernelTable* table_for(int math_mode)
+{
+    return math_mode == KT_MATH_FAST ? kt_kernel_table_fast() : kt_kernel_table_exact();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-side scalars of the reference
+// ---------------------------------------------------------------------------------------------------------
+extern "C" double kt_kerr_horizon(double a) { return 1 + 1 * std::sqrt((1 - a) * (1 + a)); } // kerr.h:13-20
+
+extern "C" double kt_kerr_isco(double a, int sign)
+{
+    // kerr.h:22-32: A and B are held in float and the closing expression is evaluated in float
+    const float A = (float)(1. + std::pow(1. - a * a, 1. / 3.) * (std::pow(1. + a, 1. / 3.) + std::pow(1. - a, 1. / 3.)));
+    const float B = (float)std::sqrt(3. * a * a + (double)(A * A));
+    const float lhs = 3 + B;
+    const float inner = (3 - A) * (3 + A + 2 * B);
+    const float res = lhs - (float)sign * sqrtf(inner);
+    return (double)res;
+}
+
+extern "C" void kt_tracer_init(kt_tracer* tr, double spin, double precision)
+{
+    tr->spin = spin;
+    tr->horizon = kt_kerr_horizon(spin);
+    tr->precision = precision;
+    tr->theta_precision = KT_THETA_PRECISION;
+    tr->max_tstep = KT_MAXDT;
+    tr->max_phistep = KT_MAXDPHI;
+    tr->maxtstep_rlim = KT_MAXDT_RLIM;
+    tr->rk45_tol = 1e-8;
+}
+
+extern "C" int64_t kt_pointsource_count(const kt_pointsource* s, int32_t* n_cosalpha, int32_t* n_beta)
+{
+    const double fa = ((s->cosalphamax - s->cosalpha0) / s->dcosalpha) + 1;
+    const double fb = ((s->betamax - s->beta0) / s->dbeta) + 1;
+    if (n_cosalpha) *n_cosalpha = (int32_t)fa;
+    if (n_beta) *n_beta = (int32_t)fb;
+    // the reference truncates the double product into `int num_rays`; we keep 64 bits so that grids beyond
+    // 2^31 rays (which the reference cannot represent) remain addressable by the fused paths
+    return (int64_t)(fa * fb);
+}
+
+extern "C" int64_t kt_imageplane_count(const kt_imageplane* p, int32_t* Nx, int32_t* Ny)
+{
+    const double fx = ((p->xmax - p->x0) / p->dx) + 1;
+    const double fy = ((p->ymax - p->y0) / p->dy) + 1;
+    if (Nx) *Nx = (int32_t)fx;
+    if (Ny) *Ny = (int32_t)fy;
+    const int64_t slots = (int64_t)(fx * fy);
+    return p->bundles ? slots * 5 : slots;
+}
+
+static int make_params(TraceParams& P, const kt_tracer* tr, const kt_stop* stop, const kt_run* run)
+{
+    if (!tr) return fail(KT_ERR_INVALID, "null tracer");
+    memset(&P, 0, sizeof(P));
+    P.tr = *tr;
+    if (stop) P.stop = *stop;
+    if (run) {
+        if (run->integrator == KT_EULER)
+            return fail(KT_ERR_UNSUPPORTED, "Integrator::Euler is not offloaded (reference CPU path only)");
+        if (run->integrator != KT_RK4 && run->integrator != KT_RK45) return fail(KT_ERR_INVALID, "unknown integrator %d", run->integrator);
+        P.integrator = run->integrator;
+        P.rlim = run->r_max;
+        P.steplim = run->steplim > 0 ? run->steplim : (run->integrator == KT_RK45 ? KT_RK45_STEPLIM : KT_STEPLIM); // raytracer.cpp:80
+    }
+    if (stop && (stop->kind < KT_STOP_THETALIM || stop->kind > KT_STOP_FLATPLANE)) return fail(KT_ERR_INVALID, "unknown stop kind %d", stop->kind);
+    const double a = tr->spin;
+    P.a = a;
+    P.two_a = 2 * a;
+    P.two_a_a = 2 * a * a;
+    P.aa = a * a;
+    P.nranks = 1;
+    return KT_OK;
+}
+
+static void set_work(TraceParams& P, kt_ctx* c, long long count, const kt_shard* sh)
+{
+    P.queue = c->d_queue;
+    if (!sh) {
+        P.begin = 0; P.end = count; P.rank = 0; P.nranks = 1; P.chunk = 65536; P.n_work = count;
+        return;
+    }
+    long long b = sh->begin < 0 ? 0 : sh->begin;
+    long long e = sh->end > count ? count : sh->end;
+    if (e < b) e = b;
+    P.begin = b; P.end = e;
+    P.nranks = sh->nranks > 1 ? sh->nranks : 1;
+    P.rank = P.nranks > 1 ? sh->rank : 0;
+    P.chunk = sh->chunk > 0 ? sh->chunk : 65536;
+    if (P.nranks == 1) { P.n_work = e - b; return; }
+    const long long total = e - b;
+    const long long nchunks = (total + P.chunk - 1) / P.chunk;
+    const long long mine = nchunks > P.rank ? (nchunks - P.rank + P.nranks - 1) / P.nranks : 0;
+    P.n_work = mine * P.chunk;   // upper bound; the kernel drops ordinals that map beyond `end`
+}
+
+// source-frame tetrad of calculate_constants (raytracer.cpp:632-650), evaluated once on the host with the
+// reference's expressions and the host libm (so these numbers are bit-identical to the CPU path)
+static void make_ps_frame(PointSourceFrame& F, const kt_tracer* tr, const kt_pointsource* s)
+{
+    const double a = tr->spin, r = s->pos[1], th = s->pos[2], V = s->V;
+    const double rho2 = r * r + (a * std::cos(th)) * (a * std::cos(th));
+    const double del = r * r - 2 * r + a * a;
+    const double sig2 = (r * r + a * a) * (r * r + a * a) - a * a * del * std::sin(th) * std::sin(th);
+    const double e2nu = rho2 * del / sig2;
+    const double e2psi = sig2 * std::sin(th) * std::sin(th) / rho2;
+    const double omega = 2 * a * r / sig2;
+    memset(&F, 0, sizeof(F));
+    for (int i = 0; i < 4; i++) F.pos[i] = s->pos[i];
+    F.E = s->E;
+    F.V = V;
+    F.et0 = (1 / std::sqrt(e2nu)) / std::sqrt(1 - (V - omega) * (V - omega) * e2psi / e2nu);
+    F.et3 = (1 / std::sqrt(e2nu)) * V / std::sqrt(1 - (V - omega) * (V - omega) * e2psi / e2nu);
+    F.e10 = (V - omega) * std::sqrt(e2psi / e2nu) / std::sqrt(e2nu - (V - omega) * (V - omega) * e2psi);
+    F.e13 = (1 / std::sqrt(e2nu * e2psi)) * (e2nu + V * omega * e2psi - omega * omega * e2psi) /
+            std::sqrt(e2nu - (V - omega) * (V - omega) * e2psi);
+    F.e22 = -1 / std::sqrt(rho2);
+    F.e31 = std::sqrt(del / rho2);
+    F.rho2 = rho2;
+    F.sn = std::sin(th);
+    F.cs = std::cos(th);
+    F.tn = std::tan(th);
+    F.cosalpha0 = s->cosalpha0; F.dcosalpha = s->dcosalpha; F.cosalphamax = s->cosalphamax;
+    F.beta0 = s->beta0; F.dbeta = s->dbeta; F.betamax = s->betamax;
+    int32_t na, nb;
+    kt_pointsource_count(s, &na, &nb);
+    F.n_cosalpha = na;
+    F.n_beta = nb;
+}
+
+static void make_plane_frame(PlaneFrame& F, const kt_imageplane* p)
+{
+    memset(&F, 0, sizeof(F));
+    F.D = p->dist;
+    F.incl = p->incl_deg * M_PI / 180;   // imageplane.cpp:23
+    F.phi0 = p->phi0;
+    F.x0 = p->x0; F.y0 = p->y0; F.dy = p->dy;
+    F.eps_x = p->eps_frac * p->dx;       // imageplane_bundles.h:151-152
+    F.eps_y = p->eps_frac * p->dy;
+    F.sin_i = std::sin(F.incl);
+    F.cos_i = std::cos(F.incl);
+    int32_t nx, ny;
+    kt_imageplane_count(p, &nx, &ny);
+    F.Nx = nx; F.Ny = ny;
+    F.bundles = p->bundles;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device-resident ray sets
+// ---------------------------------------------------------------------------------------------------------
+extern "C" kt_rayset* kt_rayset_create(kt_ctx* c, int64_t n)
+{
+    if (ctx_bind(c) != KT_OK) return nullptr;
+    if (n < 0) { fail(KT_ERR_INVALID, "negative ray count"); return nullptr; }
+    kt_rayset* rs = new (std::nothrow) kt_rayset;
+    if (!rs) return nullptr;
+    rs->ctx = c; rs->n = n; rs->d = nullptr;
+    if (n > 0) {
+        if (cudaMalloc(&rs->d, (size_t)n * sizeof(kt_ray)) != cudaSuccess) {
+            cudaGetLastError();
+            fail(KT_ERR_NOMEM, "device allocation of %lld rays failed", (long long)n);
+            delete rs;
+            return nullptr;
+        }
+        cudaError_t e = kt_kernel_table_exact()->rayset_reset(cfg_of(c), rs->d, n);
+        c->launches++;
+        if (e != cudaSuccess) {
+            fail(KT_ERR_CUDA, "rayset reset: %s", cudaGetErrorString(e));
+            cudaFree(rs->d);
+            delete rs;
+            return nullptr;
+        }
+    }
+    return rs;
+}
+
+extern "C" void kt_rayset_destroy(kt_rayset* rs)
+{
+    if (!rs) return;
+    cudaSetDevice(rs->ctx->device);
+    cudaStreamSynchronize(rs->ctx->stream);
+    if (rs->d) cudaFree(rs->d);
+    delete rs;
+}
+
+extern "C" int64_t kt_rayset_count(const kt_rayset* rs) { return rs ? rs->n : 0; }
+extern "C" void* kt_rayset_device_ptr(kt_rayset* rs) { return rs ? rs->d : nullptr; }
+
+extern "C" int kt_rayset_upload(kt_rayset* rs, const kt_ray* host, int64_t n)
+{
+    if (!rs || !host || n < 0 || n > rs->n) return fail(KT_ERR_INVALID, "bad upload arguments");
+    if (int rc = ctx_bind(rs->ctx)) return rc;
+    KT_CUDA(cudaMemcpyAsync(rs->d, host, (size_t)n * sizeof(kt_ray), cudaMemcpyHostToDevice, rs->ctx->stream));
+    KT_CUDA(cudaStreamSynchronize(rs->ctx->stream));
+    return KT_OK;
+}
+
+extern "C" int kt_rayset_download(kt_rayset* rs, kt_ray* host, int64_t n)
+{
+    if (!rs || !host || n < 0 || n > rs->n) return fail(KT_ERR_INVALID, "bad download arguments");
+    if (int rc = ctx_bind(rs->ctx)) return rc;
+    KT_CUDA(cudaMemcpyAsync(host, rs->d, (size_t)n * sizeof(kt_ray), cudaMemcpyDeviceToHost, rs->ctx->stream));
+    KT_CUDA(cudaStreamSynchronize(rs->ctx->stream));
+    return KT_OK;
+}
+
+// ---- operations on a raw device pointer (shared by the rayset and the host-buffer entry points) ----------
+static int dev_init_pointsource(kt_ctx* c, kt_ray* d, long long n, const kt_tracer* tr, const kt_pointsource* s)
+{
+    if (!s) return fail(KT_ERR_INVALID, "null source");
+    TraceParams P;
+    if (int rc = make_params(P, tr, nullptr, nullptr)) return rc;
+    PointSourceFrame F;
+    make_ps_frame(F, tr, s);
+    KT_CUDA(kt_kernel_table_exact()->init_pointsource(cfg_of(c), d, n, P, F));
+    c->launches++;
+    return KT_OK;
+}
+
+static int dev_init_imageplane(kt_ctx* c, kt_ray* d, long long n, const kt_tracer* tr, const kt_imageplane* p)
+{
+    if (!p) return fail(KT_ERR_INVALID, "null image plane");
+    TraceParams P;
+    if (int rc = make_params(P, tr, nullptr, nullptr)) return rc;
+    PlaneFrame F;
+    make_plane_frame(F, p);
+    KT_CUDA(kt_kernel_table_exact()->init_imageplane(cfg_of(c), d, n, P, F));
+    c->launches++;
+    return KT_OK;
+}
+
+static int dev_redshift_start(kt_ctx* c, kt_ray* d, long long n, const kt_tracer* tr, double V, int reverse, int projradius)
+{
+    TraceParams P;
+    if (int rc = make_params(P, tr, nullptr, nullptr)) return rc;
+    if (n <= 0) return KT_OK;
+    if (V == -1) {
+        // raytracer.cpp:391-394 overwrites the by-value V inside the loop: ray 0 defines it for every ray
+        kt_ray first;
+        KT_CUDA(cudaMemcpyAsync(&first, d, sizeof(kt_ray), cudaMemcpyDeviceToHost, c->stream));
+        KT_CUDA(cudaStreamSynchronize(c->stream));
+        const double a = reverse ? -1 * tr->spin : tr->spin;
+        if (projradius) V = 1 / (a + first.r * std::sin(first.theta) * std::sqrt(first.r * std::sin(first.theta)));
+        else V = 1 / (a + first.r * std::sqrt(first.r));
+    }
+    KT_CUDA(kt_kernel_table_exact()->redshift_start(cfg_of(c), d, n, P, V, reverse, projradius));
+    c->launches++;
+    return KT_OK;
+}
+
+static int dev_trace(kt_ctx* c, kt_ray* d, long long n, const kt_tracer* tr, const kt_stop* stop, const kt_run* run)
+{
+    if (!stop || !run) return fail(KT_ERR_INVALID, "null stop / run");
+    TraceParams P;
+    if (int rc = make_params(P, tr, stop, run)) return rc;
+    if (n <= 0) return KT_OK;
+    set_work(P, c, n, nullptr);
+    if (int rc = ensure_scratch(c, KT_NCOUNTERS * sizeof(double))) return rc;
+    KT_CUDA(cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned long long), c->stream));
+    KT_CUDA(cudaMemsetAsync(c->d_scratch, 0, KT_NCOUNTERS * sizeof(double), c->stream));
+    KT_CUDA(table_for(run->math_mode)->trace_rayset(cfg_of(c), P, d, c->d_scratch));
+    c->launches++;
+    return KT_OK;
+}
+
+static int dev_redshift(kt_ctx* c, kt_ray* d, long long n, const kt_tracer* tr, double V, int reverse, int projradius, int motion)
+{
+    TraceParams P;
+    if (int rc = make_params(P, tr, nullptr, nullptr)) return rc;
+    if (n <= 0) return KT_OK;
+    KT_CUDA(kt_kernel_table_exact()->redshift_V(cfg_of(c), d, n, P, V, reverse, projradius, motion));
+    c->launches++;
+    return KT_OK;
+}
+
+static int dev_redshift_dest(kt_ctx* c, kt_ray* d, long long n, const kt_tracer* tr, const kt_stop* stop, int reverse)
+{
+    TraceParams P;
+    if (int rc = make_params(P, tr, stop, nullptr)) return rc;
+    if (n <= 0) return KT_OK;
+    KT_CUDA(kt_kernel_table_exact()->redshift_dest(cfg_of(c), d, n, P, reverse));
+    c->launches++;
+    return KT_OK;
+}
+
+static int dev_range_phi(kt_ctx* c, kt_ray* d, long long n, double lo, double hi)
+{
+    if (n <= 0) return KT_OK;
+    KT_CUDA(kt_kernel_table_exact()->range_phi(cfg_of(c), d, n, lo, hi));
+    c->launches++;
+    return KT_OK;
+}
+
+#define RS_CHECK(rs)                                             \
+    if (!(rs)) return fail(KT_ERR_INVALID, "null ray set");       \
+    if (int rc__ = ctx_bind((rs)->ctx)) return rc__;
+
+extern "C" int kt_rayset_init_pointsource(kt_rayset* rs, const kt_tracer* tr, const kt_pointsource* s)
+{
+    RS_CHECK(rs);
+    return dev_init_pointsource(rs->ctx, rs->d, rs->n, tr, s);
+}
+extern "C" int kt_rayset_init_imageplane(kt_rayset* rs, const kt_tracer* tr, const kt_imageplane* p)
+{
+    RS_CHECK(rs);
+    return dev_init_imageplane(rs->ctx, rs->d, rs->n, tr, p);
+}
+extern "C" int kt_rayset_redshift_start(kt_rayset* rs, const kt_tracer* tr, double V, int reverse, int projradius)
+{
+    RS_CHECK(rs);
+    return dev_redshift_start(rs->ctx, rs->d, rs->n, tr, V, reverse, projradius);
+}
+extern "C" int kt_rayset_trace(kt_rayset* rs, const kt_tracer* tr, const kt_stop* stop, const kt_run* run)
+{
+    RS_CHECK(rs);
+    return dev_trace(rs->ctx, rs->d, rs->n, tr, stop, run);
+}
+extern "C" int kt_rayset_redshift(kt_rayset* rs, const kt_tracer* tr, double V, int reverse, int projradius, int motion)
+{
+    RS_CHECK(rs);
+    return dev_redshift(rs->ctx, rs->d, rs->n, tr, V, reverse, projradius, motion);
+}
+extern "C" int kt_rayset_redshift_dest(kt_rayset* rs, const kt_tracer* tr, const kt_stop* stop, int reverse)
+{
+    RS_CHECK(rs);
+    return dev_redshift_dest(rs->ctx, rs->d, rs->n, tr, stop, reverse);
+}
+extern "C" int kt_rayset_range_phi(kt_rayset* rs, double lo, double hi)
+{
+    RS_CHECK(rs);
+    return dev_range_phi(rs->ctx, rs->d, rs->n, lo, hi);
+}
+extern "C" int kt_rayset_calculate_momentum(kt_rayset* rs, const kt_tracer* tr)
+{
+    RS_CHECK(rs);
+    TraceParams P;
+    if (int rc = make_params(P, tr, nullptr, nullptr)) return rc;
+    if (rs->n <= 0) return KT_OK;
+    KT_CUDA(kt_kernel_table_exact()->calc_momentum(cfg_of(rs->ctx), rs->d, rs->n, P));
+    rs->ctx->launches++;
+    return KT_OK;
+}
+
+// ---- reductions: packed device buffer -> host structs ------------------------------------------------------
+static void unpack_counters(const double* packed, int64_t* counters)
+{
+    for (int i = 0; i < KT_NCOUNTERS; i++) counters[i] = (int64_t)llround(packed[i]);
+}
+
+static int fetch_emis(kt_ctx* c, const double* d_hist, int Nr, kt_emis_out* out)
+{
+    const size_t nd = (size_t)5 * Nr + KT_NCOUNTERS;
+    if (int rc = ensure_pinned(c, nd * sizeof(double))) return rc;
+    KT_CUDA(cudaMemcpyAsync(c->h_pinned, d_hist, nd * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    const double* h = c->h_pinned;
+    for (int i = 0; i < Nr; i++) {
+        if (out->N) out->N[i] = (int64_t)llround(h[i]);
+        if (out->flux) out->flux[i] = h[Nr + i];
+        if (out->emis) out->emis[i] = h[2 * Nr + i];
+        if (out->redshift_sum) out->redshift_sum[i] = h[3 * Nr + i];
+        if (out->time_sum) out->time_sum[i] = h[4 * Nr + i];
+    }
+    unpack_counters(h + 5 * (size_t)Nr, out->counters);
+    return KT_OK;
+}
+
+static int fetch_image(kt_ctx* c, const double* d_maps, long long npix, kt_image_out* out)
+{
+    const size_t nd = (size_t)7 * npix + KT_NCOUNTERS;
+    if (int rc = ensure_pinned(c, nd * sizeof(double))) return rc;
+    KT_CUDA(cudaMemcpyAsync(c->h_pinned, d_maps, nd * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    const double* h = c->h_pinned;
+    double* dst[6] = {out->flux, out->r, out->phi, out->enshift, out->time, out->emis};
+    for (int m = 0; m < 6; m++)
+        if (dst[m]) memcpy(dst[m], h + (size_t)m * npix, (size_t)npix * sizeof(double));
+    if (out->N)
+        for (long long i = 0; i < npix; i++) out->N[i] = (int32_t)llround(h[6 * (size_t)npix + i]);
+    unpack_counters(h + 7 * (size_t)npix, out->counters);
+    return KT_OK;
+}
+
+extern "C" int kt_rayset_bin_emissivity(kt_rayset* rs, const kt_emis_bins* b, kt_emis_out* out)
+{
+    RS_CHECK(rs);
+    if (!b || !out || b->Nr <= 0) return fail(KT_ERR_INVALID, "bad emissivity bins");
+    kt_ctx* c = rs->ctx;
+    const size_t nd = (size_t)5 * b->Nr + KT_NCOUNTERS;
+    if (int rc = ensure_scratch(c, nd * sizeof(double))) return rc;
+    KT_CUDA(cudaMemsetAsync(c->d_scratch, 0, nd * sizeof(double), c->stream));
+    if (rs->n > 0) {
+        KT_CUDA(kt_kernel_table_exact()->bin_emissivity(cfg_of(c), rs->d, rs->n, *b, std::log(b->dr), c->d_scratch));
+        c->launches++;
+    }
+    return fetch_emis(c, c->d_scratch, b->Nr, out);
+}
+
+extern "C" int kt_rayset_bin_image(kt_rayset* rs, const kt_image_bins* b, kt_image_out* out)
+{
+    RS_CHECK(rs);
+    if (!b || !out || b->img_Nx <= 0 || b->img_Ny <= 0) return fail(KT_ERR_INVALID, "bad image bins");
+    kt_ctx* c = rs->ctx;
+    const long long npix = (long long)b->img_Nx * b->img_Ny;
+    const size_t nd = (size_t)7 * npix + KT_NCOUNTERS;
+    if (int rc = ensure_scratch(c, nd * sizeof(double))) return rc;
+    KT_CUDA(cudaMemsetAsync(c->d_scratch, 0, nd * sizeof(double), c->stream));
+    if (rs->n > 0) {
+        KT_CUDA(kt_kernel_table_exact()->bin_image(cfg_of(c), rs->d, rs->n, *b, c->d_scratch));
+        c->launches++;
+    }
+    return fetch_image(c, c->d_scratch, npix, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-buffer entry points: H2D -> op -> D2H on the ctx stream (what the shim's Raytracer methods call)
+// ---------------------------------------------------------------------------------------------------------
+static int stage_in(kt_ctx* c, const kt_ray* rays, int64_t n, bool upload)
+{
+    if (!rays || n < 0) return fail(KT_ERR_INVALID, "bad ray buffer");
+    if (int rc = ctx_bind(c)) return rc;
+    if (n == 0) return KT_OK;
+    if (int rc = ensure_rays(c, (size_t)n * sizeof(kt_ray))) return rc;
+    if (upload) KT_CUDA(cudaMemcpyAsync(c->d_rays, rays, (size_t)n * sizeof(kt_ray), cudaMemcpyHostToDevice, c->stream));
+    return KT_OK;
+}
+
+static int stage_out(kt_ctx* c, kt_ray* rays, int64_t n)
+{
+    if (n == 0) return KT_OK;
+    KT_CUDA(cudaMemcpyAsync(rays, c->d_rays, (size_t)n * sizeof(kt_ray), cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    return KT_OK;
+}
+
+extern "C" int kt_trace(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, const kt_run* run, kt_ray* rays, int64_t n)
+{
+    if (int rc = stage_in(c, rays, n, true)) return rc;
+    if (int rc = dev_trace(c, c->d_rays, n, tr, stop, run)) return rc;
+    return stage_out(c, rays, n);
+}
+extern "C" int kt_redshift_start(kt_ctx* c, const kt_tracer* tr, kt_ray* rays, int64_t n, double V, int reverse, int projradius)
+{
+    if (int rc = stage_in(c, rays, n, true)) return rc;
+    if (int rc = dev_redshift_start(c, c->d_rays, n, tr, V, reverse, projradius)) return rc;
+    return stage_out(c, rays, n);
+}
+extern "C" int kt_redshift(kt_ctx* c, const kt_tracer* tr, kt_ray* rays, int64_t n, double V, int reverse, int projradius, int motion)
+{
+    if (int rc = stage_in(c, rays, n, true)) return rc;
+    if (int rc = dev_redshift(c, c->d_rays, n, tr, V, reverse, projradius, motion)) return rc;
+    return stage_out(c, rays, n);
+}
+extern "C" int kt_redshift_dest(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, kt_ray* rays, int64_t n, int reverse)
+{
+    if (int rc = stage_in(c, rays, n, true)) return rc;
+    if (int rc = dev_redshift_dest(c, c->d_rays, n, tr, stop, reverse)) return rc;
+    return stage_out(c, rays, n);
+}
+extern "C" int kt_range_phi(kt_ctx* c, kt_ray* rays, int64_t n, double lo, double hi)
+{
+    if (int rc = stage_in(c, rays, n, true)) return rc;
+    if (int rc = dev_range_phi(c, c->d_rays, n, lo, hi)) return rc;
+    return stage_out(c, rays, n);
+}
+extern "C" int kt_pointsource_init(kt_ctx* c, const kt_tracer* tr, const kt_pointsource* s, kt_ray* rays, int64_t n)
+{
+    if (int rc = stage_in(c, rays, n, false)) return rc;
+    if (int rc = dev_init_pointsource(c, c->d_rays, n, tr, s)) return rc;
+    return stage_out(c, rays, n);
+}
+extern "C" int kt_imageplane_init(kt_ctx* c, const kt_tracer* tr, const kt_imageplane* p, kt_ray* rays, int64_t n)
+{
+    if (int rc = stage_in(c, rays, n, false)) return rc;
+    if (int rc = dev_init_imageplane(c, c->d_rays, n, tr, p)) return rc;
+    return stage_out(c, rays, n);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fused paths
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int kt_pointsource_emissivity_dev(kt_ctx* c, const kt_pointsource* s, const kt_tracer* tr, const kt_stop* stop,
+                                             const kt_run* run, const kt_emis_bins* b, const kt_shard* sh, double* dev_hist)
+{
+    if (int rc = ctx_bind(c)) return rc;
+    if (!s || !stop || !run || !b || !dev_hist || b->Nr <= 0) return fail(KT_ERR_INVALID, "bad emissivity arguments");
+    TraceParams P;
+    if (int rc = make_params(P, tr, stop, run)) return rc;
+    PointSourceFrame F;
+    make_ps_frame(F, tr, s);
+    const long long count = kt_pointsource_count(s, nullptr, nullptr);
+    set_work(P, c, count, sh);
+    if (P.n_work <= 0) return KT_OK;
+    KT_CUDA(cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned long long), c->stream));
+    KT_CUDA(table_for(run->math_mode)->trace_emis(cfg_of(c), P, F, *b, std::log(b->dr), dev_hist));
+    c->launches++;
+    return KT_OK;
+}
+
+extern "C" int kt_pointsource_emissivity(kt_ctx* c, const kt_pointsource* s, const kt_tracer* tr, const kt_stop* stop,
+                                         const kt_run* run, const kt_emis_bins* b, const kt_shard* sh, kt_emis_out* out)
+{
+    if (int rc = ctx_bind(c)) return rc;
+    if (!b || !out || b->Nr <= 0) return fail(KT_ERR_INVALID, "bad emissivity arguments");
+    const size_t nd = (size_t)5 * b->Nr + KT_NCOUNTERS;
+    if (int rc = ensure_scratch(c, nd * sizeof(double))) return rc;
+    KT_CUDA(cudaMemsetAsync(c->d_scratch, 0, nd * sizeof(double), c->stream));
+    if (int rc = kt_pointsource_emissivity_dev(c, s, tr, stop, run, b, sh, c->d_scratch)) return rc;
+    return fetch_emis(c, c->d_scratch, b->Nr, out);
+}
+
+extern "C" int kt_imageplane_image_dev(kt_ctx* c, const kt_imageplane* p, const kt_tracer* tr, const kt_stop* stop,
+                                       const kt_run* run, const kt_image_bins* b, const kt_shard* sh, double* dev_maps)
+{
+    if (int rc = ctx_bind(c)) return rc;
+    if (!p || !stop || !run || !b || !dev_maps || b->img_Nx <= 0 || b->img_Ny <= 0) return fail(KT_ERR_INVALID, "bad image arguments");
+    TraceParams P;
+    if (int rc = make_params(P, tr, stop, run)) return rc;
+    PlaneFrame F;
+    make_plane_frame(F, p);
+    const long long count = kt_imageplane_count(p, nullptr, nullptr);
+    set_work(P, c, count, sh);
+    if (P.n_work <= 0) return KT_OK;
+    KT_CUDA(cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned long long), c->stream));
+    KT_CUDA(table_for(run->math_mode)->trace_image(cfg_of(c), P, F, *b, 1, dev_maps));
+    c->launches++;
+    return KT_OK;
+}
+
+extern "C" int kt_imageplane_image(kt_ctx* c, const kt_imageplane* p, const kt_tracer* tr, const kt_stop* stop, const kt_run* run,
+                                   const kt_image_bins* b, const kt_shard* sh, kt_image_out* out)
+{
+    if (int rc = ctx_bind(c)) return rc;
+    if (!b || !out || b->img_Nx <= 0 || b->img_Ny <= 0) return fail(KT_ERR_INVALID, "bad image arguments");
+    const long long npix = (long long)b->img_Nx * b->img_Ny;
+    const size_t nd = (size_t)7 * npix + KT_NCOUNTERS;
+    if (int rc = ensure_scratch(c, nd * sizeof(double))) return rc;
+    KT_CUDA(cudaMemsetAsync(c->d_scratch, 0, nd * sizeof(double), c->stream));
+    if (int rc = kt_imageplane_image_dev(c, p, tr, stop, run, b, sh, c->d_scratch)) return rc;
+    return fetch_image(c, c->d_scratch, npix, out);
+}
+
+extern "C" int kt_imageplane_rays(kt_ctx* c, const kt_imageplane* p, const kt_tracer* tr, const kt_stop* stop, const kt_run* run,
+                                  int redshift_mode, double V, int range_phi, kt_ray_min* host_out, int64_t n)
+{
+    if (int rc = ctx_bind(c)) return rc;
+    if (!p || !stop || !run || !host_out) return fail(KT_ERR_INVALID, "bad arguments");
+    TraceParams P;
+    if (int rc = make_params(P, tr, stop, run)) return rc;
+    PlaneFrame F;
+    make_plane_frame(F, p);
+    const long long count = kt_imageplane_count(p, nullptr, nullptr);
+    if (n < count) return fail(KT_ERR_INVALID, "output buffer holds %lld rays, the plane has %lld", (long long)n, count);
+    if (count <= 0) return KT_OK;
+    set_work(P, c, count, nullptr);
+    kt_image_bins B;
+    memset(&B, 0, sizeof(B));
+    B.redshift_mode = redshift_mode;
+    B.reverse = 1;
+    B.V = V;
+    const size_t out_bytes = (size_t)count * sizeof(kt_ray_min);
+    if (int rc = ensure_rays(c, out_bytes + KT_NCOUNTERS * sizeof(double))) return rc;
+    kt_ray_min* d_out = reinterpret_cast<kt_ray_min*>(c->d_rays);
+    double* d_cnt = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(c->d_rays) + out_bytes);
+    // surplus tail slots (steps = -1 in the reference) are never written by the kernel: pre-fill them
+    KT_CUDA(cudaMemsetAsync(d_out, 0, out_bytes + KT_NCOUNTERS * sizeof(double), c->stream));
+    KT_CUDA(cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned long long), c->stream));
+    KT_CUDA(table_for(run->math_mode)->trace_planerays(cfg_of(c), P, F, B, range_phi, d_out, d_cnt));
+    c->launches++;
+    KT_CUDA(cudaMemcpyAsync(host_out, d_out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    const long long live = (long long)F.Nx * F.Ny * (F.bundles ? 5 : 1);
+    for (long long i = live; i < count; i++) host_out[i].steps = -1;
+    return KT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FP64 roofline denominator
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int kt_fp64_peak(kt_ctx* c, double* tflops)
+{
+    if (int rc = ctx_bind(c)) return rc;
+    if (!tflops) return fail(KT_ERR_INVALID, "null output");
+    const int blocks = c->sm_count * 4, threads = 256, iters = 1024;
+    cudaEvent_t e0, e1;
+    KT_CUDA(cudaEventCreate(&e0));
+    KT_CUDA(cudaEventCreate(&e1));
+    const KernelTable* T = kt_kernel_table_fast();
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        KT_CUDA(cudaEventRecord(e0, c->stream));
+        KT_CUDA(T->dfma_peak(cfg_of(c), c->d_scratch, blocks, threads, iters));
+        c->launches++;
+        KT_CUDA(cudaEventRecord(e1, c->stream));
+        KT_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        KT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double fmas = (double)blocks * threads * (double)iters * 16.0 * 8.0;
+        const double tf = 2.0 * fmas / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return KT_OK;
+}
+
+// sizeof() of every POD struct of the ABI, so bindings can check their mirrors (tests/test_abi.py)
+extern "C" int kt_abi_sizeof(const char* name)
+{
+    if (!strcmp(name, "kt_ray")) return (int)sizeof(kt_ray);
+    if (!strcmp(name, "kt_ray_min")) return (int)sizeof(kt_ray_min);
+    if (!strcmp(name, "kt_stop")) return (int)sizeof(kt_stop);
+    if (!strcmp(name, "kt_tracer")) return (int)sizeof(kt_tracer);
+    if (!strcmp(name, "kt_run")) return (int)sizeof(kt_run);
+    if (!strcmp(name, "kt_pointsource")) return (int)sizeof(kt_pointsource);
+    if (!strcmp(name, "kt_imageplane")) return (int)sizeof(kt_imageplane);
+    if (!strcmp(name, "kt_shard")) return (int)sizeof(kt_shard);
+    if (!strcmp(name, "kt_emis_bins")) return (int)sizeof(kt_emis_bins);
+    if (!strcmp(name, "kt_emis_out")) return (int)sizeof(kt_emis_out);
+    if (!strcmp(name, "kt_image_bins")) return (int)sizeof(kt_image_bins);
+    if (!strcmp(name, "kt_image_out")) return (int)sizeof(kt_image_out);
+    return -1;
+}

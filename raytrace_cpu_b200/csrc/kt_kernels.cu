@@ -1,0 +1,668 @@
+// kt_kernels.cu -- IO policies, kernel instantiations and launchers.  Compiled once per arithmetic mode
+// (Makefile: -DKT_FAST=0 -fmad=false  ->  kt_kernels_exact.o ;  -DKT_FAST=1 -fmad=true  ->  kt_kernels_fast.o).
+#include "kt_kernels.h"
+#include "kt_trace.cuh"
+
+namespace kt {
+namespace KT_MODE_NS {
+
+// =========================================================================================================
+// IO policy 1: device-resident AoS ray set in, same ray set out  (Raytracer<T>::run_raytrace on `rays`)
+// =========================================================================================================
+struct RaysetIO {
+    static constexpr int ND_IN = 12, NI_IN = 8, ND_OUT = 8, NI_OUT = 9;
+    kt_ray* rays;
+    double* counters;
+    unsigned char* smem;
+
+    __device__ void block_begin() {}
+    __device__ void block_end() {}
+    __device__ double* counters_out() { return counters; }
+
+    // run_raytrace skips rays with steps < 0 or steps >= steplim: raytracer.cpp:116-117
+    __device__ bool make(const TraceParams& P, long long idx, RayIn& in, LaneCounters&)
+    {
+        const kt_ray& q = rays[idx];
+        const int st = q.steps;
+        if (st < 0 || st >= P.steplim) return false;
+        in.t = q.t; in.r = q.r; in.th = q.theta; in.ph = q.phi;
+        in.k = q.k; in.h = q.h; in.Q = q.Q;
+        in.pt = q.pt; in.pr = q.pr; in.pth = q.ptheta; in.pph = q.pphi;
+        in.emit = 0; in.step0 = 0;
+        in.steps0 = st; in.status0 = q.status;
+        in.sr = q.rdot_sign; in.sth = q.thetadot_sign; in.flips = q.rdot_flips; in.cross = q.equatorial_crossings;
+        return true;
+    }
+    __device__ void pack_in(Stage<ND_IN, NI_IN>& b, int slot, const RayIn& in)
+    {
+        b.d[0][slot] = in.t; b.d[1][slot] = in.r; b.d[2][slot] = in.th; b.d[3][slot] = in.ph;
+        b.d[4][slot] = in.k; b.d[5][slot] = in.h; b.d[6][slot] = in.Q;
+        b.d[7][slot] = in.pt; b.d[8][slot] = in.pr; b.d[9][slot] = in.pth; b.d[10][slot] = in.pph;
+        b.d[11][slot] = in.step0;
+        b.i[0][slot] = (int)(in.idx & 0xffffffffll); b.i[1][slot] = (int)(in.idx >> 32);
+        b.i[2][slot] = in.steps0; b.i[3][slot] = in.status0; b.i[4][slot] = in.sr; b.i[5][slot] = in.sth;
+        b.i[6][slot] = in.flips; b.i[7][slot] = in.cross;
+    }
+    __device__ void unpack_in(const Stage<ND_IN, NI_IN>& b, int slot, RayIn& in)
+    {
+        in.t = b.d[0][slot]; in.r = b.d[1][slot]; in.th = b.d[2][slot]; in.ph = b.d[3][slot];
+        in.k = b.d[4][slot]; in.h = b.d[5][slot]; in.Q = b.d[6][slot];
+        in.pt = b.d[7][slot]; in.pr = b.d[8][slot]; in.pth = b.d[9][slot]; in.pph = b.d[10][slot];
+        in.step0 = b.d[11][slot];
+        in.idx = ((long long)b.i[1][slot] << 32) | (unsigned int)b.i[0][slot];
+        in.steps0 = b.i[2][slot]; in.status0 = b.i[3][slot]; in.sr = b.i[4][slot]; in.sth = b.i[5][slot];
+        in.flips = b.i[6][slot]; in.cross = b.i[7][slot];
+        in.emit = 0; in.alpha = 0; in.beta = 0;
+    }
+    __device__ void pack_out(Stage<ND_OUT, NI_OUT>& b, int slot, const RayOut& o)
+    {
+        b.d[0][slot] = o.t; b.d[1][slot] = o.r; b.d[2][slot] = o.th; b.d[3][slot] = o.ph;
+        b.d[4][slot] = o.pt; b.d[5][slot] = o.pr; b.d[6][slot] = o.pth; b.d[7][slot] = o.pph;
+        b.i[0][slot] = (int)(o.idx & 0xffffffffll); b.i[1][slot] = (int)(o.idx >> 32);
+        b.i[2][slot] = o.steps0; b.i[3][slot] = o.steps; b.i[4][slot] = o.status; b.i[5][slot] = o.sr;
+        b.i[6][slot] = o.sth; b.i[7][slot] = o.flips; b.i[8][slot] = o.cross;
+    }
+    __device__ void unpack_out(const Stage<ND_OUT, NI_OUT>& b, int slot, RayOut& o)
+    {
+        o.t = b.d[0][slot]; o.r = b.d[1][slot]; o.th = b.d[2][slot]; o.ph = b.d[3][slot];
+        o.pt = b.d[4][slot]; o.pr = b.d[5][slot]; o.pth = b.d[6][slot]; o.pph = b.d[7][slot];
+        o.idx = ((long long)b.i[1][slot] << 32) | (unsigned int)b.i[0][slot];
+        o.steps0 = b.i[2][slot]; o.steps = b.i[3][slot]; o.status = b.i[4][slot]; o.sr = b.i[5][slot];
+        o.sth = b.i[6][slot]; o.flips = b.i[7][slot]; o.cross = b.i[8][slot];
+    }
+    // write-back: raytracer.cpp:952-967
+    __device__ void retire(const TraceParams&, const RayOut& o, LaneCounters& c)
+    {
+        kt_ray& q = rays[o.idx];
+        q.t = o.t; q.r = o.r; q.theta = o.th; q.phi = o.ph;
+        q.pt = o.pt; q.pr = o.pr; q.ptheta = o.pth; q.pphi = o.pph;
+        q.rdot_sign = o.sr; q.thetadot_sign = o.sth; q.rdot_flips = o.flips; q.equatorial_crossings = o.cross;
+        q.status = o.status;
+        int st = o.steps0;
+        if (o.steps > 0) st += o.steps;
+        if (o.status & KT_STATUS_STEPLIM) st = -st;
+        q.steps = st;
+        count_terminal(c, o.steps, o.status);
+    }
+};
+
+// =========================================================================================================
+// Shared pieces of the fused (source -> reduction) policies
+// =========================================================================================================
+
+// final steps value as the reference leaves it in rays[].steps (steps0 == 0 for freshly generated rays)
+__device__ __forceinline__ int final_steps(int steps, int status)
+{
+    int st = 0;
+    if (steps > 0) st = steps;
+    if (status & KT_STATUS_STEPLIM) st = -st;
+    return st;
+}
+
+// =========================================================================================================
+// IO policy 2: PointSource -> emissivity histogram  (emissivity{,_rd}.cpp:88-126 in one kernel)
+// =========================================================================================================
+struct EmisIO {
+    static constexpr int ND_IN = 5, NI_IN = 3, ND_OUT = 7, NI_OUT = 3;
+    PointSourceFrame F;
+    kt_emis_bins B;
+    double log_dr;     // log(dr) evaluated by the host libm
+    double* hist;      // global: double[5*Nr + KT_NCOUNTERS]
+    int use_smem_hist;
+    unsigned char* smem;
+
+    __device__ double* block_hist() { return reinterpret_cast<double*>(smem); }
+    __device__ void block_begin()
+    {
+        if (use_smem_hist) {
+            double* hb = block_hist();
+            for (int i = threadIdx.x; i < 5 * B.Nr; i += blockDim.x) hb[i] = 0.0;
+        }
+        __syncthreads();
+    }
+    // one atomic per non-empty bin per CTA
+    __device__ void block_end()
+    {
+        __syncthreads();
+        if (use_smem_hist) {
+            const double* hb = block_hist();
+            for (int i = threadIdx.x; i < 5 * B.Nr; i += blockDim.x) {
+                const double v = hb[i];
+                if (v != 0.0) atomicAdd(&hist[i], v);
+            }
+        }
+    }
+    __device__ double* counters_out() { return hist + 5 * (long long)B.Nr; }
+
+    __device__ bool make(const TraceParams& P, long long idx, RayIn& in, LaneCounters&)
+    {
+        RaySeed sd;
+        if (!pointsource_seed(F, P.a, idx, sd)) return false;
+        in.t = sd.t; in.r = sd.r; in.th = sd.th; in.ph = sd.ph;
+        in.k = sd.k; in.h = sd.h; in.Q = sd.Q;
+        in.sr = sd.sr; in.sth = sd.sth;
+        in.flips = 0; in.cross = 0; in.steps0 = 0; in.status0 = 0;
+        in.pt = in.pr = in.pth = in.pph = 0; in.step0 = 0;
+        // PointSource::redshift_start() -> Raytracer::redshift_start(velocity): pointsource.cpp:67-73
+        in.emit = observed_energy_V(P, F.V, false, false, 0, sd.r, sd.th, sd.k, sd.h, sd.Q, sd.sr, sd.sth);
+        return true;
+    }
+    __device__ void pack_in(Stage<ND_IN, NI_IN>& b, int slot, const RayIn& in)
+    {
+        b.d[0][slot] = in.k; b.d[1][slot] = in.h; b.d[2][slot] = in.Q; b.d[3][slot] = in.emit; b.d[4][slot] = in.step0;
+        b.i[0][slot] = (int)(in.idx & 0xffffffffll); b.i[1][slot] = (int)(in.idx >> 32);
+        b.i[2][slot] = (in.sr > 0 ? 1 : 0) | (in.sth > 0 ? 2 : 0);
+    }
+    __device__ void unpack_in(const Stage<ND_IN, NI_IN>& b, int slot, RayIn& in)
+    {
+        in.t = F.pos[0]; in.r = F.pos[1]; in.th = F.pos[2]; in.ph = F.pos[3];
+        in.k = b.d[0][slot]; in.h = b.d[1][slot]; in.Q = b.d[2][slot]; in.emit = b.d[3][slot]; in.step0 = b.d[4][slot];
+        in.idx = ((long long)b.i[1][slot] << 32) | (unsigned int)b.i[0][slot];
+        const int sg = b.i[2][slot];
+        in.sr = (sg & 1) ? 1 : -1; in.sth = (sg & 2) ? 1 : -1;
+        in.flips = 0; in.cross = 0; in.steps0 = 0; in.status0 = 0;
+        in.pt = in.pr = in.pth = in.pph = 0; in.alpha = in.beta = 0;
+    }
+    __device__ void pack_out(Stage<ND_OUT, NI_OUT>& b, int slot, const RayOut& o)
+    {
+        b.d[0][slot] = o.t; b.d[1][slot] = o.r; b.d[2][slot] = o.th;
+        b.d[3][slot] = o.k; b.d[4][slot] = o.h; b.d[5][slot] = o.Q; b.d[6][slot] = o.emit;
+        b.i[0][slot] = o.steps; b.i[1][slot] = o.status; b.i[2][slot] = (o.sr > 0 ? 1 : 0) | (o.sth > 0 ? 2 : 0);
+    }
+    __device__ void unpack_out(const Stage<ND_OUT, NI_OUT>& b, int slot, RayOut& o)
+    {
+        o.t = b.d[0][slot]; o.r = b.d[1][slot]; o.th = b.d[2][slot];
+        o.k = b.d[3][slot]; o.h = b.d[4][slot]; o.Q = b.d[5][slot]; o.emit = b.d[6][slot];
+        o.steps = b.i[0][slot]; o.status = b.i[1][slot];
+        const int sg = b.i[2][slot];
+        o.sr = (sg & 1) ? 1 : -1; o.sth = (sg & 2) ? 1 : -1;
+    }
+    // redshift + the app's binning loop: raytracer.cpp:480-600, emissivity.cpp:96-126, emissivity_rd.cpp:108-138
+    __device__ void retire(const TraceParams& P, const RayOut& o, LaneCounters& c)
+    {
+        count_terminal(c, o.steps, o.status);
+        const int st = final_steps(o.steps, o.status);
+        if (!(st > 0)) return;
+        double recv;
+        if (B.redshift_mode == KT_REDSHIFT_DEST) recv = observed_energy_dest(P, false, o.r, o.th, o.k, o.h, o.Q, o.sr, o.sth);
+        else recv = observed_energy_V(P, B.V, false, false, 0, o.r, o.th, o.k, o.h, o.Q, o.sr, o.sth);
+        const double g = o.emit / recv;
+        bool hit;
+        if (B.hit_filter == KT_HIT_THETA) hit = o.th >= B.theta_lim - 1e-3;
+        else hit = o.r * cos(o.th) < 1E-2;
+        if (hit && g > 0 && o.r >= B.r_isco) {
+            const int ir = B.logbin ? (int)(log(o.r / B.r_min) / log_dr) : (int)((o.r - B.r_min) / B.dr);
+            if (ir >= 0 && ir < B.Nr) {
+                double* hb = use_smem_hist ? block_hist() : hist;
+                const int Nr = B.Nr;
+                atomicAdd(&hb[ir], 1.0);
+                atomicAdd(&hb[Nr + ir], 1 / (B.n_primary * pow(g, 1.0)));
+                atomicAdd(&hb[2 * Nr + ir], 1 / pow(g, B.gamma));
+                atomicAdd(&hb[3 * Nr + ir], g);
+                atomicAdd(&hb[4 * Nr + ir], o.t);
+            }
+            c.disc++;
+        }
+    }
+};
+
+// =========================================================================================================
+// IO policy 3: ImagePlane / ImagePlaneBundles -> image maps or compact per-ray results
+//   IMAGE = true : imageplane_disc_image{,_rd,_isco}.cpp:109-161 (7 sum maps, global atomics: one ray per
+//                  pixel when img_N == N, so contention is nil)
+//   IMAGE = false: caustic_discplane.cpp:209-217 (trace + redshift; kt_ray_min per ray)
+// =========================================================================================================
+template <bool IMAGE>
+struct PlaneIO {
+    static constexpr int ND_IN = 7, NI_IN = 3, ND_OUT = 7, NI_OUT = 7;
+    PlaneFrame F;
+    kt_image_bins B;      // IMAGE only (redshift_mode / reverse / V also used by the ray variant)
+    double* maps;         // IMAGE: double[7*npix + KT_NCOUNTERS]
+    kt_ray_min* out;      // !IMAGE
+    double* counters;     // !IMAGE
+    int do_range_phi;
+    unsigned char* smem;
+
+    __device__ void block_begin() {}
+    __device__ void block_end() {}
+    __device__ double* counters_out() { return IMAGE ? maps + 7ll * B.img_Nx * B.img_Ny : counters; }
+
+    __device__ bool make(const TraceParams& P, long long idx, RayIn& in, LaneCounters&)
+    {
+        double x, y;
+        bool guard_b;
+        if (!plane_slot(F, idx, x, y, guard_b)) return false;
+        RaySeed sd;
+        plane_seed(F, P.a, x, y, guard_b, sd, nullptr);
+        in.t = 0; in.r = sd.r; in.th = sd.th; in.ph = sd.ph;
+        in.k = sd.k; in.h = sd.h; in.Q = sd.Q;
+        in.sr = sd.sr; in.sth = sd.sth;
+        in.flips = 0; in.cross = 0; in.steps0 = 0; in.status0 = 0;
+        in.pt = in.pr = in.pth = in.pph = 0; in.step0 = 0;
+        // ImagePlane::redshift_start() -> Raytracer::redshift_start(0, true): imageplane.cpp:124-130
+        in.emit = observed_energy_V(P, 0.0, true, false, 0, sd.r, sd.th, sd.k, sd.h, sd.Q, sd.sr, sd.sth);
+        return true;
+    }
+    __device__ void pack_in(Stage<ND_IN, NI_IN>& b, int slot, const RayIn& in)
+    {
+        b.d[0][slot] = in.r; b.d[1][slot] = in.th; b.d[2][slot] = in.ph;
+        b.d[3][slot] = in.h; b.d[4][slot] = in.Q; b.d[5][slot] = in.emit; b.d[6][slot] = in.step0;
+        b.i[0][slot] = (int)(in.idx & 0xffffffffll); b.i[1][slot] = (int)(in.idx >> 32);
+        b.i[2][slot] = (in.sr > 0 ? 1 : 0) | (in.sth > 0 ? 2 : 0);
+    }
+    __device__ void unpack_in(const Stage<ND_IN, NI_IN>& b, int slot, RayIn& in)
+    {
+        in.t = 0; in.r = b.d[0][slot]; in.th = b.d[1][slot]; in.ph = b.d[2][slot];
+        in.k = 1; in.h = b.d[3][slot]; in.Q = b.d[4][slot]; in.emit = b.d[5][slot]; in.step0 = b.d[6][slot];
+        in.idx = ((long long)b.i[1][slot] << 32) | (unsigned int)b.i[0][slot];
+        const int sg = b.i[2][slot];
+        in.sr = (sg & 1) ? 1 : -1; in.sth = (sg & 2) ? 1 : -1;
+        in.flips = 0; in.cross = 0; in.steps0 = 0; in.status0 = 0;
+        in.pt = in.pr = in.pth = in.pph = 0; in.alpha = in.beta = 0;
+    }
+    __device__ void pack_out(Stage<ND_OUT, NI_OUT>& b, int slot, const RayOut& o)
+    {
+        b.d[0][slot] = o.t; b.d[1][slot] = o.r; b.d[2][slot] = o.th; b.d[3][slot] = o.ph;
+        b.d[4][slot] = o.h; b.d[5][slot] = o.Q; b.d[6][slot] = o.emit;
+        b.i[0][slot] = (int)(o.idx & 0xffffffffll); b.i[1][slot] = (int)(o.idx >> 32);
+        b.i[2][slot] = o.steps; b.i[3][slot] = o.status; b.i[4][slot] = (o.sr > 0 ? 1 : 0) | (o.sth > 0 ? 2 : 0);
+        b.i[5][slot] = o.flips; b.i[6][slot] = o.cross;
+    }
+    __device__ void unpack_out(const Stage<ND_OUT, NI_OUT>& b, int slot, RayOut& o)
+    {
+        o.t = b.d[0][slot]; o.r = b.d[1][slot]; o.th = b.d[2][slot]; o.ph = b.d[3][slot];
+        o.k = 1; o.h = b.d[4][slot]; o.Q = b.d[5][slot]; o.emit = b.d[6][slot];
+        o.idx = ((long long)b.i[1][slot] << 32) | (unsigned int)b.i[0][slot];
+        o.steps = b.i[2][slot]; o.status = b.i[3][slot];
+        const int sg = b.i[4][slot];
+        o.sr = (sg & 1) ? 1 : -1; o.sth = (sg & 2) ? 1 : -1;
+        o.flips = b.i[5][slot]; o.cross = b.i[6][slot];
+    }
+    __device__ double powerlaw3(double r) const
+    {
+        // imageplane_disc_image.cpp:20-28
+        if (r < B.rb1) return pow(r, -1 * B.q1);
+        else if (r < B.rb2) return pow(B.rb1, B.q2 - B.q1) * pow(r, -1 * B.q2);
+        else return pow(B.rb1, B.q2 - B.q1) * pow(B.rb2, B.q3 - B.q2) * pow(r, -1 * B.q3);
+    }
+    __device__ void retire(const TraceParams& P, const RayOut& o, LaneCounters& c)
+    {
+        count_terminal(c, o.steps, o.status);
+        const int st = final_steps(o.steps, o.status);
+        const bool rev = B.reverse != 0;
+        double recv;
+        if (B.redshift_mode == KT_REDSHIFT_DEST) recv = observed_energy_dest(P, rev, o.r, o.th, o.k, o.h, o.Q, o.sr, o.sth);
+        else recv = observed_energy_V(P, B.V, rev, false, 0, o.r, o.th, o.k, o.h, o.Q, o.sr, o.sth);
+        const double g = rev ? recv / o.emit : o.emit / recv;
+        const double phi = do_range_phi ? wrap_phi(o.ph, st, -1 * KT_PI, KT_PI) : o.ph;
+        if (!IMAGE) {
+            kt_ray_min m;
+            m.r = o.r; m.theta = o.th; m.phi = phi; m.t = o.t; m.redshift = g;
+            m.steps = st; m.status = o.status; m.rdot_flips = o.flips; m.equatorial_crossings = o.cross;
+            out[o.idx] = m;
+            return;
+        }
+        if (!(st > 0)) return;
+        bool hit;
+        if (B.hit_filter == KT_HIT_DEST) hit = (o.status & KT_STATUS_DEST) && o.r < B.r_disc && g > 0;
+        else if (B.hit_filter == KT_HIT_THETA) hit = o.th >= B.theta_lim - 1e-3 && o.r >= B.r_isco && o.r < B.r_disc && g > 0;
+        else hit = o.r * cos(o.th) < 1E-2 && o.r >= B.r_isco && o.r < B.r_disc && g > 0;
+        if (!hit) return;
+        double x, y;
+        bool guard_b;
+        plane_slot(F, o.idx, x, y, guard_b);   // Ray::alpha / Ray::beta (imageplane.cpp:117-118)
+        // bin-edge arithmetic exactly as imageplane_disc_image.cpp:134-135 (no FMA: plain sub and div)
+        int ix = (int)(__ddiv_rn(__dsub_rn(x, B.x0), B.img_dx));
+        int iy = (int)(__ddiv_rn(__dsub_rn(y, B.y0), B.img_dy));
+        if (B.flip_image) iy = B.img_Ny - iy - 1;
+        if (ix >= 0 && ix < B.img_Nx && iy >= 0 && iy < B.img_Ny) {
+            const long long npix = (long long)B.img_Nx * B.img_Ny;
+            const long long p = (long long)ix * B.img_Ny + iy;
+            const double em = powerlaw3(o.r);
+            atomicAdd(&maps[p], em / pow(g, 3.0));
+            atomicAdd(&maps[npix + p], o.r);
+            atomicAdd(&maps[2 * npix + p], phi);
+            atomicAdd(&maps[3 * npix + p], 1. / g);
+            atomicAdd(&maps[4 * npix + p], o.t);
+            atomicAdd(&maps[5 * npix + p], em);
+            atomicAdd(&maps[6 * npix + p], 1.0);
+            c.disc++;
+        }
+    }
+};
+
+// =========================================================================================================
+// One-thread-per-ray kernels on device-resident ray sets (the serial O(n) loops of the reference)
+// =========================================================================================================
+__global__ void k_rayset_reset(kt_ray* rays, long long n)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    kt_ray z = {};
+    z.steps = -1;
+    rays[i] = z;
+}
+
+__global__ void k_init_pointsource(kt_ray* rays, long long n, TraceParams P, PointSourceFrame F)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    kt_ray q = {};
+    q.steps = -1;
+    RaySeed sd;
+    if (pointsource_seed(F, P.a, i, sd)) {
+        q.t = sd.t; q.r = sd.r; q.theta = sd.th; q.phi = sd.ph;
+        q.k = sd.k; q.h = sd.h; q.Q = sd.Q;
+        q.rdot_sign = sd.sr; q.thetadot_sign = sd.sth;
+        q.alpha = sd.alpha; q.beta = sd.beta;
+        q.steps = 0;
+    }
+    rays[i] = q;
+}
+
+__global__ void k_init_imageplane(kt_ray* rays, long long n, TraceParams P, PlaneFrame F)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    kt_ray q = {};
+    q.steps = -1;
+    double x, y;
+    bool guard_b;
+    if (plane_slot(F, i, x, y, guard_b)) {
+        RaySeed sd;
+        Mom p0;
+        plane_seed(F, P.a, x, y, guard_b, sd, &p0);
+        q.t = sd.t; q.r = sd.r; q.theta = sd.th; q.phi = sd.ph;
+        q.pt = p0.pt; q.pr = p0.pr; q.ptheta = p0.pth; q.pphi = p0.pph;
+        q.k = sd.k; q.h = sd.h; q.Q = sd.Q;
+        q.rdot_sign = sd.sr; q.thetadot_sign = sd.sth;
+        q.alpha = sd.alpha; q.beta = sd.beta;
+        q.steps = 0;
+    }
+    rays[i] = q;
+}
+
+// redshift_start: raytracer.cpp:342-417 (V already resolved by the host if it was -1, see kt_api.cu)
+__global__ void k_redshift_start(kt_ray* rays, long long n, TraceParams P, double V, int reverse, int projradius)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    kt_ray& q = rays[i];
+    q.emit = observed_energy_V(P, V, reverse != 0, projradius != 0, 0, q.r, q.theta, q.k, q.h, q.Q, q.rdot_sign,
+                               q.thetadot_sign);
+}
+
+// redshift(V, ...): raytracer.cpp:420-447
+__global__ void k_redshift_V(kt_ray* rays, long long n, TraceParams P, double V, int reverse, int projradius, int motion)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    kt_ray& q = rays[i];
+    const double recv = observed_energy_V(P, V, reverse != 0, projradius != 0, motion, q.r, q.theta, q.k, q.h, q.Q,
+                                          q.rdot_sign, q.thetadot_sign);
+    q.redshift = reverse ? recv / q.emit : q.emit / recv;
+}
+
+// redshift(dest, ...): raytracer.cpp:450-477
+__global__ void k_redshift_dest(kt_ray* rays, long long n, TraceParams P, int reverse)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    kt_ray& q = rays[i];
+    const double recv = observed_energy_dest(P, reverse != 0, q.r, q.theta, q.k, q.h, q.Q, q.rdot_sign, q.thetadot_sign);
+    q.redshift = reverse ? recv / q.emit : q.emit / recv;
+}
+
+__global__ void k_range_phi(kt_ray* rays, long long n, double lo, double hi)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rays[i].phi = wrap_phi(rays[i].phi, rays[i].steps, lo, hi);
+}
+
+// calculate_momentum: raytracer.cpp:704-753
+__global__ void k_calc_momentum(kt_ray* rays, long long n, TraceParams P)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    kt_ray& q = rays[i];
+    const Mom m = momenta(P, q.k, q.h, q.Q, q.k * P.a, q.rdot_sign, q.thetadot_sign, q.r, q.theta);
+    q.pt = m.pt; q.pr = m.pr; q.ptheta = m.pth; q.pphi = m.pph;
+}
+
+// the apps' binning loops over an already traced + redshifted ray set
+__global__ void k_bin_emissivity(const kt_ray* rays, long long n, kt_emis_bins B, double log_dr, double* hist)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    LaneCounters c;
+    c.clear();
+    if (i < n) {
+        const kt_ray q = rays[i];
+        c.slots++;
+        if (q.steps != -1 || q.status != 0) count_terminal(c, q.steps, q.status);
+        if (q.steps > 0) {
+            bool hit;
+            if (B.hit_filter == KT_HIT_THETA) hit = q.theta >= B.theta_lim - 1e-3;
+            else hit = q.r * cos(q.theta) < 1E-2;
+            if (hit && q.redshift > 0 && q.r >= B.r_isco) {
+                const int ir = B.logbin ? (int)(log(q.r / B.r_min) / log_dr) : (int)((q.r - B.r_min) / B.dr);
+                if (ir >= 0 && ir < B.Nr) {
+                    const int Nr = B.Nr;
+                    atomicAdd(&hist[ir], 1.0);
+                    atomicAdd(&hist[Nr + ir], 1 / (B.n_primary * pow(q.redshift, 1.0)));
+                    atomicAdd(&hist[2 * Nr + ir], 1 / pow(q.redshift, B.gamma));
+                    atomicAdd(&hist[3 * Nr + ir], q.redshift);
+                    atomicAdd(&hist[4 * Nr + ir], q.t);
+                }
+                c.disc++;
+            }
+        }
+    }
+    flush_counters(c, hist + 5ll * B.Nr);
+}
+
+__global__ void k_bin_image(const kt_ray* rays, long long n, kt_image_bins B, double* maps)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    LaneCounters c;
+    c.clear();
+    const long long npix = (long long)B.img_Nx * B.img_Ny;
+    if (i < n) {
+        const kt_ray q = rays[i];
+        c.slots++;
+        if (q.steps != -1 || q.status != 0) count_terminal(c, q.steps, q.status);
+        if (q.steps > 0) {
+            const double g = q.redshift;
+            bool hit;
+            if (B.hit_filter == KT_HIT_DEST) hit = (q.status & KT_STATUS_DEST) && q.r < B.r_disc && g > 0;
+            else if (B.hit_filter == KT_HIT_THETA) hit = q.theta >= B.theta_lim - 1e-3 && q.r >= B.r_isco && q.r < B.r_disc && g > 0;
+            else hit = q.r * cos(q.theta) < 1E-2 && q.r >= B.r_isco && q.r < B.r_disc && g > 0;
+            if (hit) {
+                int ix = (int)(__ddiv_rn(__dsub_rn(q.alpha, B.x0), B.img_dx));
+                int iy = (int)(__ddiv_rn(__dsub_rn(q.beta, B.y0), B.img_dy));
+                if (B.flip_image) iy = B.img_Ny - iy - 1;
+                if (ix >= 0 && ix < B.img_Nx && iy >= 0 && iy < B.img_Ny) {
+                    const long long p = (long long)ix * B.img_Ny + iy;
+                    double em;
+                    if (q.r < B.rb1) em = pow(q.r, -1 * B.q1);
+                    else if (q.r < B.rb2) em = pow(B.rb1, B.q2 - B.q1) * pow(q.r, -1 * B.q2);
+                    else em = pow(B.rb1, B.q2 - B.q1) * pow(B.rb2, B.q3 - B.q2) * pow(q.r, -1 * B.q3);
+                    atomicAdd(&maps[p], em / pow(g, 3.0));
+                    atomicAdd(&maps[npix + p], q.r);
+                    atomicAdd(&maps[2 * npix + p], q.phi);
+                    atomicAdd(&maps[3 * npix + p], 1. / g);
+                    atomicAdd(&maps[4 * npix + p], q.t);
+                    atomicAdd(&maps[5 * npix + p], em);
+                    atomicAdd(&maps[6 * npix + p], 1.0);
+                    c.disc++;
+                }
+            }
+        }
+    }
+    flush_counters(c, maps + 7 * npix);
+}
+
+// FP64 FMA peak: 8 independent dependent-chains per thread, 4096 FMAs each
+__global__ void k_dfma_peak(double* out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+        }
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) out[0] = s;
+}
+
+// =========================================================================================================
+// Launchers
+// =========================================================================================================
+constexpr int TRACE_THREADS = 128;
+
+template <int INTEG, class IO, int MINB>
+static cudaError_t launch_trace(const LaunchCfg& cfg, const TraceParams& P, IO io, size_t extra_smem)
+{
+    auto kern = trace_persistent<INTEG, IO, TRACE_THREADS, MINB>;
+    constexpr int WARPS = TRACE_THREADS / 32;
+    const size_t smem = (sizeof(Stage<IO::ND_IN, IO::NI_IN>) + sizeof(Stage<IO::ND_OUT, IO::NI_OUT>)) * WARPS + extra_smem;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TRACE_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (long long)cfg.sm_count * per_sm;
+    // never launch more lanes than there is work
+    const long long need = (P.n_work + TRACE_THREADS - 1) / TRACE_THREADS;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, TRACE_THREADS, smem, cfg.stream>>>(P, io);
+    return cudaGetLastError();
+}
+
+template <class IO>
+static cudaError_t launch_trace_any(const LaunchCfg& cfg, const TraceParams& P, IO io, size_t extra_smem)
+{
+    const int minb = cfg.min_blocks;
+    if (P.integrator == KT_RK45) {
+        return launch_trace<KT_RK45, IO, 3>(cfg, P, io, extra_smem);
+    }
+    if (minb == 3) return launch_trace<KT_RK4, IO, 3>(cfg, P, io, extra_smem);
+    if (minb == 5) return launch_trace<KT_RK4, IO, 5>(cfg, P, io, extra_smem);
+    return launch_trace<KT_RK4, IO, 4>(cfg, P, io, extra_smem);
+}
+
+static inline unsigned nblocks(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+static cudaError_t l_trace_rayset(const LaunchCfg& cfg, const TraceParams& P, kt_ray* rays, double* counters)
+{
+    RaysetIO io;
+    io.rays = rays; io.counters = counters; io.smem = nullptr;
+    return launch_trace_any(cfg, P, io, 0);
+}
+
+static cudaError_t l_trace_emis(const LaunchCfg& cfg, const TraceParams& P, const PointSourceFrame& F, const kt_emis_bins& B,
+                                double log_dr, double* hist)
+{
+    EmisIO io;
+    io.F = F; io.B = B; io.log_dr = log_dr; io.hist = hist; io.smem = nullptr;
+    const size_t hist_bytes = (size_t)5 * B.Nr * sizeof(double);
+    io.use_smem_hist = hist_bytes <= 64 * 1024;
+    return launch_trace_any(cfg, P, io, io.use_smem_hist ? hist_bytes : 0);
+}
+
+static cudaError_t l_trace_image(const LaunchCfg& cfg, const TraceParams& P, const PlaneFrame& F, const kt_image_bins& B,
+                                 int do_range_phi, double* maps)
+{
+    PlaneIO<true> io;
+    io.F = F; io.B = B; io.maps = maps; io.out = nullptr; io.counters = nullptr; io.do_range_phi = do_range_phi; io.smem = nullptr;
+    return launch_trace_any(cfg, P, io, 0);
+}
+
+static cudaError_t l_trace_planerays(const LaunchCfg& cfg, const TraceParams& P, const PlaneFrame& F, const kt_image_bins& B,
+                                     int do_range_phi, kt_ray_min* out, double* counters)
+{
+    PlaneIO<false> io;
+    io.F = F; io.B = B; io.maps = nullptr; io.out = out; io.counters = counters; io.do_range_phi = do_range_phi; io.smem = nullptr;
+    return launch_trace_any(cfg, P, io, 0);
+}
+
+static cudaError_t l_rayset_reset(const LaunchCfg& cfg, kt_ray* rays, long long n)
+{
+    k_rayset_reset<<<nblocks(n, 256), 256, 0, cfg.stream>>>(rays, n);
+    return cudaGetLastError();
+}
+static cudaError_t l_init_pointsource(const LaunchCfg& cfg, kt_ray* rays, long long n, const TraceParams& P, const PointSourceFrame& F)
+{
+    k_init_pointsource<<<nblocks(n, 128), 128, 0, cfg.stream>>>(rays, n, P, F);
+    return cudaGetLastError();
+}
+static cudaError_t l_init_imageplane(const LaunchCfg& cfg, kt_ray* rays, long long n, const TraceParams& P, const PlaneFrame& F)
+{
+    k_init_imageplane<<<nblocks(n, 128), 128, 0, cfg.stream>>>(rays, n, P, F);
+    return cudaGetLastError();
+}
+static cudaError_t l_redshift_start(const LaunchCfg& cfg, kt_ray* rays, long long n, const TraceParams& P, double V, int reverse, int projradius)
+{
+    k_redshift_start<<<nblocks(n, 128), 128, 0, cfg.stream>>>(rays, n, P, V, reverse, projradius);
+    return cudaGetLastError();
+}
+static cudaError_t l_redshift_V(const LaunchCfg& cfg, kt_ray* rays, long long n, const TraceParams& P, double V, int reverse, int projradius, int motion)
+{
+    k_redshift_V<<<nblocks(n, 128), 128, 0, cfg.stream>>>(rays, n, P, V, reverse, projradius, motion);
+    return cudaGetLastError();
+}
+static cudaError_t l_redshift_dest(const LaunchCfg& cfg, kt_ray* rays, long long n, const TraceParams& P, int reverse)
+{
+    k_redshift_dest<<<nblocks(n, 128), 128, 0, cfg.stream>>>(rays, n, P, reverse);
+    return cudaGetLastError();
+}
+static cudaError_t l_range_phi(const LaunchCfg& cfg, kt_ray* rays, long long n, double lo, double hi)
+{
+    k_range_phi<<<nblocks(n, 256), 256, 0, cfg.stream>>>(rays, n, lo, hi);
+    return cudaGetLastError();
+}
+static cudaError_t l_calc_momentum(const LaunchCfg& cfg, kt_ray* rays, long long n, const TraceParams& P)
+{
+    k_calc_momentum<<<nblocks(n, 128), 128, 0, cfg.stream>>>(rays, n, P);
+    return cudaGetLastError();
+}
+static cudaError_t l_bin_emissivity(const LaunchCfg& cfg, const kt_ray* rays, long long n, const kt_emis_bins& B, double log_dr, double* hist)
+{
+    k_bin_emissivity<<<nblocks(n, 256), 256, 0, cfg.stream>>>(rays, n, B, log_dr, hist);
+    return cudaGetLastError();
+}
+static cudaError_t l_bin_image(const LaunchCfg& cfg, const kt_ray* rays, long long n, const kt_image_bins& B, double* maps)
+{
+    k_bin_image<<<nblocks(n, 256), 256, 0, cfg.stream>>>(rays, n, B, maps);
+    return cudaGetLastError();
+}
+static cudaError_t l_dfma_peak(const LaunchCfg& cfg, double* out, int blocks, int threads, int iters)
+{
+    k_dfma_peak<<<blocks, threads, 0, cfg.stream>>>(out, iters);
+    return cudaGetLastError();
+}
+
+}  // namespace KT_MODE_NS
+}  // namespace kt
+
+#if KT_FAST
+#define KT_TABLE_NAME kt_kernel_table_fast
+#else
+#define KT_TABLE_NAME kt_kernel_table_exact
+#endif
+
+extern "C" const kt::KernelTable* KT_TABLE_NAME()
+{
+    static const kt::KernelTable table = {
+        kt::KT_MODE_NS::l_trace_rayset, kt::KT_MODE_NS::l_trace_emis, kt::KT_MODE_NS::l_trace_image, kt::KT_MODE_NS::l_trace_planerays,
+        kt::KT_MODE_NS::l_rayset_reset, kt::KT_MODE_NS::l_init_pointsource, kt::KT_MODE_NS::l_init_imageplane,
+        kt::KT_MODE_NS::l_redshift_start, kt::KT_MODE_NS::l_redshift_V, kt::KT_MODE_NS::l_redshift_dest, kt::KT_MODE_NS::l_range_phi, kt::KT_MODE_NS::l_calc_momentum,
+        kt::KT_MODE_NS::l_bin_emissivity, kt::KT_MODE_NS::l_bin_image, kt::KT_MODE_NS::l_dfma_peak,
+    };
+    return &table;
+}

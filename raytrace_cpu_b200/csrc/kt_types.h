@@ -1,0 +1,49 @@
+// kt_types.h -- POD parameter blocks shared by the host API (kt_api.cu) and the kernels (both arithmetic modes).
+#pragma once
+#include <cstdint>
+
+#include "../../include/kerrtrace.h"
+
+namespace kt {
+
+// Per-launch constants (kernel argument -> constant bank).
+struct TraceParams {
+    kt_tracer tr;
+    kt_stop stop;
+    double rlim;
+    int steplim;
+    int integrator;
+    // loop invariants pre-multiplied exactly as the reference's expressions associate: 2*a, (2*a)*a, a*a
+    double a, two_a, two_a_a, aa;
+    // work queue
+    unsigned long long* queue;
+    long long n_work;   // number of work ordinals this launch hands out
+    // shard mapping: ordinal q -> ray index
+    long long begin, end, chunk;
+    int rank, nranks;
+};
+
+// Source-frame tetrad of a point source; depends only on the source position, so the HOST evaluates it once
+// (kt_api.cu: make_ps_frame) with the reference's expressions (raytracer.cpp:632-650) and ships the numbers.
+struct PointSourceFrame {
+    double pos[4];
+    double E;
+    double et0, et3, e10, e13, e22, e31;
+    double rho2, sn, cs, tn;  // rho^2, sin/cos/tan(theta) at the source
+    double cosalpha0, dcosalpha, cosalphamax;
+    double beta0, dbeta, betamax;
+    double V;
+    long long n_beta;
+    long long n_cosalpha;
+};
+
+struct PlaneFrame {
+    double D, incl, phi0;
+    double x0, y0, dy;        // x uses dy as well (imageplane.cpp:43)
+    double eps_x, eps_y;
+    double sin_i, cos_i;      // host-evaluated sin/cos(incl)
+    long long Nx, Ny;
+    int bundles;
+};
+
+}  // namespace kt
