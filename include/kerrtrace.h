@@ -32,6 +32,7 @@ extern "C" {
 #define KT_ERR_CUDA (-2)        /* CUDA runtime error (message has the cudaError string) */
 #define KT_ERR_NOMEM (-3)       /* host or device allocation failed */
 #define KT_ERR_UNSUPPORTED (-4) /* valid in the reference but not offloaded (Euler, ray-path dumping) */
+#define KT_ERR_TIMEOUT (-5)     /* the optional watchdog fired: a trace kernel abandoned its launch */
 
 /* ---- ray status bit flags: raytracer.h:58-63 ---- */
 #define KT_STATUS_DEST (1 << 0)
@@ -136,7 +137,7 @@ typedef struct kt_imageplane {
 typedef struct kt_shard {
     int64_t begin, end;
     int32_t rank, nranks;
-    int64_t chunk; /* <= 0: 65536 */
+    int64_t chunk; /* <= 0: automatic (about 256 chunks per rank, a multiple of 32 in [32, 65536]) */
 } kt_shard;
 
 /* Emissivity binning: emissivity.cpp:57-61,96-126; emissivity_rd.cpp:112-137. */
@@ -216,6 +217,11 @@ int kt_fp64_peak(kt_ctx*, double* tflops);
 /* tuning: resident 128-thread CTAs per SM the trace kernel is built for (3, 4 or 5; 0 = default).  Also
  * read from the environment variable KT_MIN_BLOCKS at kt_create(). */
 int kt_set_min_blocks(kt_ctx*, int min_blocks);
+/* Optional watchdog for the persistent trace kernels (seconds; 0 = off, the default; also read from the
+ * environment variable KT_TIMEOUT_S).  When armed, a kernel that runs longer abandons its launch and the
+ * next synchronising call (or kt_aborted) returns KT_ERR_TIMEOUT. */
+int kt_set_timeout(kt_ctx*, double seconds);
+int kt_aborted(kt_ctx*);
 /* pinned host memory for the host-buffer entry points (plain malloc'ed buffers work too, only slower) */
 void* kt_host_alloc(size_t bytes);
 void kt_host_free(void*);

@@ -71,6 +71,13 @@ class Context:
     def set_min_blocks(self, n):
         check(self.L.kt_set_min_blocks(self.h, int(n)))
 
+    def set_timeout(self, seconds):
+        """Arm (seconds > 0) or disarm the watchdog of the persistent trace kernels."""
+        check(self.L.kt_set_timeout(self.h, float(seconds)))
+
+    def check_aborted(self):
+        check(self.L.kt_aborted(self.h))
+
     def fp64_peak_tflops(self):
         v = C.c_double()
         check(self.L.kt_fp64_peak(self.h, C.byref(v)))

@@ -56,6 +56,7 @@ struct kt_ctx {
     size_t pinned_bytes = 0;
     long long launches = 0;
     int min_blocks = 0;
+    double timeout_s = 0;              // watchdog for the persistent kernels (0 = off)
 };
 
 struct kt_rayset {
@@ -143,7 +144,8 @@ extern "C" kt_ctx* kt_create(int device)
     cudaDeviceProp prop;
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&c->d_queue, sizeof(unsigned long long)) != cudaSuccess) {
+        cudaMalloc(&c->d_queue, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(c->d_queue, 0, 2 * sizeof(unsigned long long)) != cudaSuccess) {
         fail(KT_ERR_CUDA, "context creation failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete c;
         return nullptr;
@@ -152,6 +154,8 @@ extern "C" kt_ctx* kt_create(int device)
     c->stream = c->own_stream;
     const char* mb = getenv("KT_MIN_BLOCKS");
     c->min_blocks = mb ? atoi(mb) : 0;
+    const char* to = getenv("KT_TIMEOUT_S");
+    c->timeout_s = to ? atof(to) : 0;
     if (ensure_scratch(c, 1 << 20) != KT_OK || ensure_pinned(c, 1 << 20) != KT_OK) {
         kt_destroy(c);
         return nullptr;
@@ -195,6 +199,27 @@ extern "C" int kt_set_min_blocks(kt_ctx* c, int mb)
     return KT_OK;
 }
 
+extern "C" int kt_set_timeout(kt_ctx* c, double seconds)
+{
+    if (!c) return fail(KT_ERR_INVALID, "null context");
+    c->timeout_s = seconds;
+    return KT_OK;
+}
+
+// synchronise and report (then clear) whether a watchdog-armed kernel abandoned its launch
+extern "C" int kt_aborted(kt_ctx* c)
+{
+    if (int rc = ctx_bind(c)) return rc;
+    int flag = 0;
+    KT_CUDA(cudaMemcpyAsync(&flag, c->d_queue + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    if (flag) {
+        KT_CUDA(cudaMemsetAsync(c->d_queue + 1, 0, sizeof(unsigned long long), c->stream));
+        return fail(KT_ERR_TIMEOUT, "trace kernel exceeded the %.1f s watchdog and abandoned its launch: results are incomplete", c->timeout_s);
+    }
+    return KT_OK;
+}
+
 extern "C" void* kt_host_alloc(size_t bytes)
 {
     void* p = nullptr;
@@ -209,6 +234,8 @@ extern "C" void kt_host_free(void* p)
 {
     if (p) cudaFreeHost(p);
 }
+
+extern "C" int kt_aborted(kt_ctx* c);
 
 static LaunchCfg cfg_of(kt_ctx* c)
 {
@@ -300,6 +327,8 @@ static int make_params(TraceParams& P, const kt_tracer* tr, const kt_stop* stop,
 static void set_work(TraceParams& P, kt_ctx* c, long long count, const kt_shard* sh)
 {
     P.queue = c->d_queue;
+    P.abort_flag = reinterpret_cast<int*>(c->d_queue + 1);
+    P.timeout_ns = c->timeout_s > 0 ? (unsigned long long)(c->timeout_s * 1e9) : 0ull;
     if (!sh) {
         P.begin = 0; P.end = count; P.rank = 0; P.nranks = 1; P.chunk = 65536; P.n_work = count;
         return;
@@ -310,9 +339,16 @@ static void set_work(TraceParams& P, kt_ctx* c, long long count, const kt_shard*
     P.begin = b; P.end = e;
     P.nranks = sh->nranks > 1 ? sh->nranks : 1;
     P.rank = P.nranks > 1 ? sh->rank : 0;
-    P.chunk = sh->chunk > 0 ? sh->chunk : 65536;
-    if (P.nranks == 1) { P.n_work = e - b; return; }
     const long long total = e - b;
+    if (sh->chunk > 0) {
+        P.chunk = sh->chunk;
+    } else {
+        // auto: ~256 chunks per rank so that every rank samples the whole cost range, 32 <= chunk <= 65536
+        long long c = total / ((long long)P.nranks * 256);
+        c = (c / 32) * 32;
+        P.chunk = c < 32 ? 32 : (c > 65536 ? 65536 : c);
+    }
+    if (P.nranks == 1) { P.n_work = e - b; return; }
     const long long nchunks = (total + P.chunk - 1) / P.chunk;
     const long long mine = nchunks > P.rank ? (nchunks - P.rank + P.nranks - 1) / P.nranks : 0;
     P.n_work = mine * P.chunk;   // upper bound; the kernel drops ordinals that map beyond `end`
@@ -586,7 +622,7 @@ static int fetch_emis(kt_ctx* c, const double* d_hist, int Nr, kt_emis_out* out)
         if (out->time_sum) out->time_sum[i] = h[4 * Nr + i];
     }
     unpack_counters(h + 5 * (size_t)Nr, out->counters);
-    return KT_OK;
+    return c->timeout_s > 0 ? kt_aborted(c) : KT_OK;
 }
 
 static int fetch_image(kt_ctx* c, const double* d_maps, long long npix, kt_image_out* out)
@@ -602,7 +638,7 @@ static int fetch_image(kt_ctx* c, const double* d_maps, long long npix, kt_image
     if (out->N)
         for (long long i = 0; i < npix; i++) out->N[i] = (int32_t)llround(h[6 * (size_t)npix + i]);
     unpack_counters(h + 7 * (size_t)npix, out->counters);
-    return KT_OK;
+    return c->timeout_s > 0 ? kt_aborted(c) : KT_OK;
 }
 
 extern "C" int kt_rayset_bin_emissivity(kt_rayset* rs, const kt_emis_bins* b, kt_emis_out* out)
@@ -654,7 +690,7 @@ static int stage_out(kt_ctx* c, kt_ray* rays, int64_t n)
     if (n == 0) return KT_OK;
     KT_CUDA(cudaMemcpyAsync(rays, c->d_rays, (size_t)n * sizeof(kt_ray), cudaMemcpyDeviceToHost, c->stream));
     KT_CUDA(cudaStreamSynchronize(c->stream));
-    return KT_OK;
+    return c->timeout_s > 0 ? kt_aborted(c) : KT_OK;
 }
 
 extern "C" int kt_trace(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, const kt_run* run, kt_ray* rays, int64_t n)
@@ -795,7 +831,7 @@ extern "C" int kt_imageplane_rays(kt_ctx* c, const kt_imageplane* p, const kt_tr
     KT_CUDA(cudaStreamSynchronize(c->stream));
     const long long live = (long long)F.Nx * F.Ny * (F.bundles ? 5 : 1);
     for (long long i = live; i < count; i++) host_out[i].steps = -1;
-    return KT_OK;
+    return c->timeout_s > 0 ? kt_aborted(c) : KT_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------

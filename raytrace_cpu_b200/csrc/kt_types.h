@@ -21,6 +21,10 @@ struct TraceParams {
     // shard mapping: ordinal q -> ray index
     long long begin, end, chunk;
     int rank, nranks;
+    // watchdog: when timeout_ns != 0 every warp polls %globaltimer and abandons the launch (setting *abort_flag)
+    // once it has run longer than that -- a safety net so a bug can never wedge the GPU
+    unsigned long long timeout_ns;
+    int* abort_flag;
 };
 
 // Source-frame tetrad of a point source; depends only on the source position, so the HOST evaluates it once

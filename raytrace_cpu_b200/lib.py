@@ -20,7 +20,7 @@ class KerrtraceError(RuntimeError):
 EXPORTS = [
     "kt_device_count", "kt_create", "kt_destroy", "kt_last_error", "kt_version", "kt_set_stream", "kt_synchronize",
     "kt_sm_count", "kt_kernel_launches", "kt_fp64_peak", "kt_set_min_blocks", "kt_host_alloc", "kt_host_free",
-    "kt_abi_sizeof", "kt_tracer_init", "kt_kerr_horizon", "kt_kerr_isco", "kt_pointsource_count", "kt_imageplane_count",
+    "kt_abi_sizeof", "kt_set_timeout", "kt_aborted", "kt_tracer_init", "kt_kerr_horizon", "kt_kerr_isco", "kt_pointsource_count", "kt_imageplane_count",
     "kt_rayset_create", "kt_rayset_destroy", "kt_rayset_count", "kt_rayset_device_ptr", "kt_rayset_upload",
     "kt_rayset_download", "kt_rayset_init_pointsource", "kt_rayset_init_imageplane", "kt_rayset_redshift_start",
     "kt_rayset_trace", "kt_rayset_redshift", "kt_rayset_redshift_dest", "kt_rayset_range_phi",
@@ -68,6 +68,8 @@ def load():
     proto("kt_host_alloc", vp, C.c_size_t)
     proto("kt_host_free", None, vp)
     proto("kt_abi_sizeof", i32, C.c_char_p)
+    proto("kt_set_timeout", i32, vp, d)
+    proto("kt_aborted", i32, vp)
     proto("kt_tracer_init", None, TR, d, d)
     proto("kt_kerr_horizon", d, d)
     proto("kt_kerr_isco", d, d, i32)

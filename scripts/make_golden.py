@@ -1,0 +1,97 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libref_oracle.so, built by
+oracle/Makefile from /root/reference) and tests/golden/emissivity_rd_app.dat from the reference's own
+emissivity_rd application compiled out of tree.  Run in the build container (needs /root/reference):
+
+    python scripts/make_golden.py
+
+The reference ships no golden vectors, so these fixtures -- outputs of the reference
+itself on deterministic grids -- are what pins the oracle and the CUDA path on machines without /root/reference.
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from raytrace_cpu_b200 import _abi as A  # noqa: E402
+import oracle_bindings as ob  # noqa: E402
+from golden_cases import CASES, build_source  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REF = "/root/reference"
+
+
+def run_case(ref, case):
+    src = build_source(case)
+    if case["source"] == "point":
+        h = ref.pointsource(src, case["spin"], A.TOL)
+    else:
+        h = ref.imageplane(src, case["spin"], A.PRECISION)
+        # the reference never initialises these two counters for image planes
+        rr = h.rays(copy=False)
+        rr["rdot_flips"][:] = 0
+        rr["equatorial_crossings"][:] = 0
+    if "rk45_tol" in case:
+        h.set_rk45_tol(case["rk45_tol"])
+    h.redshift_start()
+    init = h.rays()
+    stop = ob.make_stop(**case["stop"])
+    run = ob.make_run(case["integrator"], r_max=case["r_max"], steplim=case.get("steplim", -1))
+    h.run(stop, run)
+    reverse = case["source"] != "point"
+    if case["redshift"] == "V":
+        h.redshift(-1.0, reverse)
+    else:
+        h.redshift_dest(stop, reverse)
+    if case.get("range_phi", True):
+        h.range_phi()
+    return init, h.rays()
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    ref = ob.Ref()
+    for name, case in CASES.items():
+        init, final = run_case(ref, case)
+        used = final["steps"] != -1
+        # zero the fields the reference leaves uninitialised in unused slots so the fixture is deterministic
+        for arr in (init, final):
+            for f in arr.dtype.names:
+                if f not in ("steps", "status"):
+                    arr[f][~used] = 0
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), init=init, final=final)
+        print(f"{name}: {len(final)} slots, {int(used.sum())} rays, status histogram "
+              f"{ {int(s): int((final['status'][used] == s).sum()) for s in np.unique(final['status'][used])} }")
+
+    # scalars the reference prints
+    scal = {"spins": np.array([0.0, 0.1, 0.5, 0.9, 0.998, -0.5, -0.998])}
+    scal["isco_pro"] = np.array([ref.kerr_isco(a, +1) for a in scal["spins"]])
+    scal["isco_retro"] = np.array([ref.kerr_isco(a, -1) for a in scal["spins"]])
+    scal["horizon"] = np.array([ref.kerr_horizon(a) for a in scal["spins"]])
+    np.savez(os.path.join(GOLDEN, "scalars.npz"), **scal)
+
+    # the reference's own emissivity_rd application, end to end (text output, 7 columns)
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "emissivity_rd")
+        subprocess.run(["/usr/bin/g++", "-O2", "-fopenmp", "-ffp-contract=off", "-w", f"-I{REF}/src", f"-I{REF}/src/raytracer",
+                        f"{REF}/src/emissivity/emissivity_rd.cpp", f"{REF}/src/raytracer/raytracer.cpp",
+                        f"{REF}/src/raytracer/pointsource.cpp", "-o", exe], check=True)
+        # --parfile keeps a dangling c_str() in the app: use its default relative path instead
+        os.makedirs(os.path.join(tmp, "par"))
+        os.makedirs(os.path.join(tmp, "bin"))
+        par = os.path.join(tmp, "par", "emissivity_rd.par")
+        out = os.path.join(GOLDEN, "emissivity_rd_app.dat")
+        with open(par, "w") as f:
+            f.write(f"outfile = {out}\ntheta_lim = 1.5707963\nsource = 0 10 1E-3 1.5707\nV = 0\nspin = 0.998\n"
+                    "dcosalpha = 0.02\ndbeta = 0.02\nNr = 30\nlogbin_r = 1\nshow_progress = 0\n")
+        subprocess.run([exe], check=True, stdout=subprocess.DEVNULL, cwd=os.path.join(tmp, "bin"))
+        print("emissivity_rd_app.dat:", sum(1 for _ in open(out)), "lines")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,230 @@
+"""Pins the CPU oracle (oracle/kerr_oracle.c) to the reference.
+
+* against the committed golden fixtures (outputs of the unmodified reference, scripts/make_golden.py):
+  BIT-EXACT for every ray field, on every machine;
+* against the live reference build oracle/_ref/libref_oracle.so where it exists (build container; the prebuilt
+  .so also travels to the GPU box): bit-exact on larger grids and on the API corner cases;
+* against the text output of the reference's own emissivity_rd application (binning loop + area division).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from raytrace_cpu_b200 import _abi as A
+import oracle_bindings as ob
+from golden_cases import CASES, R_ISCO, SPIN, build_source, tracer_for
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FLOAT_FIELDS = [n for n in A.RAY_DTYPE.names if A.RAY_DTYPE[n].kind == "f"]
+INT_FIELDS = [n for n in A.RAY_DTYPE.names if A.RAY_DTYPE[n].kind == "i"]
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return ob.Oracle()
+
+
+def assert_bit_identical(got, want, skip=()):
+    assert (got["steps"] == want["steps"]).all()
+    assert (got["status"] == want["status"]).all()
+    used = want["steps"] != -1
+    for f in INT_FIELDS:
+        if f not in skip:
+            assert (got[f][used] == want[f][used]).all(), f
+    for f in FLOAT_FIELDS:
+        if f not in skip:
+            bad = ~ob.same_bits(got[f][used], want[f][used])
+            assert not bad.any(), f"{f}: {int(bad.sum())} rays differ"
+
+
+def run_oracle_case(orc, case):
+    src = build_source(case)
+    tr = tracer_for(case, orc.tracer)
+    point = case["source"] == "point"
+    rays = orc.pointsource_rays(tr, src) if point else orc.imageplane_rays(tr, src)
+    orc.redshift_start(rays, tr, src.V if point else 0.0, not point)
+    init = rays.copy()
+    stop = ob.make_stop(**case["stop"])
+    run = ob.make_run(case["integrator"], r_max=case["r_max"], steplim=case.get("steplim", -1))
+    orc.trace(rays, tr, stop, run)
+    if case["redshift"] == "V":
+        orc.redshift(rays, tr, -1.0, not point)
+    else:
+        orc.redshift_dest(rays, tr, stop, not point)
+    if case.get("range_phi", True):
+        orc.range_phi(rays)
+    return init, rays
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_reproduces_golden_fixture_bit_for_bit(orc, name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    init, final = run_oracle_case(orc, CASES[name])
+    assert len(final) == len(g["final"])
+    assert_bit_identical(init, g["init"], skip=("redshift",))     # redshift is not yet defined before the trace
+    assert_bit_identical(final, g["final"])
+
+
+def test_golden_scalars(orc):
+    s = np.load(os.path.join(GOLDEN, "scalars.npz"))
+    for a, ip, ir, hz in zip(s["spins"], s["isco_pro"], s["isco_retro"], s["horizon"]):
+        assert orc.kerr_isco(a, +1) == ip and orc.kerr_isco(a, -1) == ir
+        assert orc.kerr_horizon(a) == hz or (np.isnan(hz) and np.isnan(orc.kerr_horizon(a)))
+    assert orc.kerr_isco(SPIN) == R_ISCO
+
+
+def test_oracle_binning_matches_reference_emissivity_rd_app(orc):
+    """tests/golden/emissivity_rd_app.dat is the 7-column output of the reference's own emissivity_rd binary
+    (text_output.h: scientific, precision 8).  Columns: r, area, N, flux/area, emis/area, <g>, <t>."""
+    dat = np.genfromtxt(os.path.join(GOLDEN, "emissivity_rd_app.dat"))
+    assert dat.shape == (30, 7)
+    src = ob.make_pointsource([0, 10, 1e-3, 1.5707], 0.02, 0.02, cosalpha0=-0.995, cosalphamax=0.995, beta0=-np.pi, betamax=np.pi)
+    tr = orc.tracer(SPIN, A.TOL)
+    rays = orc.pointsource_rays(tr, src)
+    orc.redshift_start(rays, tr, 0.0)
+    stop = ob.make_stop(A.STOP_FLATDISC, theta_lim=1.5707963)
+    orc.trace(rays, tr, stop, ob.make_run(A.RK4))
+    orc.range_phi(rays)
+    orc.redshift_dest(rays, tr, stop)
+    import raytrace_cpu_b200 as K
+    bins = K.emissivity_bins(SPIN, Nr=30, src=src, hit_filter=A.HIT_THETA, redshift_mode=A.REDSHIFT_DEST, theta_lim=1.5707963)
+    out = orc.bin_emissivity(rays, bins)
+    r_bins = K.api.bin_radii(bins)
+    np.testing.assert_allclose(r_bins, dat[:, 0], rtol=2e-8)
+    assert (out.N == dat[:, 2].astype(np.int64)).all()            # ray counts per annulus: exact
+    area = dat[:, 1]
+    full = out.N > 0
+    np.testing.assert_allclose(out.flux[full] / area[full], dat[full, 3], rtol=2e-8)
+    np.testing.assert_allclose(out.emis[full] / area[full], dat[full, 4], rtol=2e-8)
+    np.testing.assert_allclose(out.redshift_sum[full] / out.N[full], dat[full, 5], rtol=2e-8)
+    np.testing.assert_allclose(out.time_sum[full] / out.N[full], dat[full, 6], rtol=2e-8)
+    assert np.isnan(dat[~full, 5]).all()                           # 0/0 in empty bins
+    if ob.ref_available():                                         # the area column is the reference's integrate_disc_area
+        ref = ob.Ref()
+        dr = bins.dr
+        want = np.array([ref.integrate_disc_area(r, r * dr, SPIN) for r in r_bins])
+        np.testing.assert_allclose(want, area, rtol=2e-8)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# live reference (skipped where oracle/_ref was not built)
+# ---------------------------------------------------------------------------------------------------------
+needs_ref = pytest.mark.skipif(not ob.ref_available(), reason="oracle/_ref/libref_oracle.so not built")
+
+
+@needs_ref
+@pytest.mark.parametrize("integ", [A.RK4, A.RK45])
+@pytest.mark.parametrize("stopk", [A.STOP_THETALIM, A.STOP_FLATDISC, A.STOP_ISCODISC])
+def test_live_reference_lamppost_5167(orc, integ, stopk):
+    """The reference's own emissivity_rk45_test grid (5 167 slots), every integrator x stop-surface pair."""
+    ref = ob.Ref()
+    src = ob.make_pointsource([0, 5, 1e-3, 0], 0.05, 0.05, cosalpha0=-0.995, cosalphamax=0.995, beta0=-np.pi, betamax=np.pi)
+    tr = orc.tracer(SPIN, A.TOL)
+    h = ref.pointsource(src, SPIN)
+    rays = orc.pointsource_rays(tr, src)
+    assert len(rays) == h.count() == 5167
+    h.redshift_start()
+    orc.redshift_start(rays, tr, 0.0)
+    stop = ob.make_stop(stopk, r_isco=R_ISCO, r_out=50.0)
+    run = ob.make_run(integ)
+    h.run(stop, run)
+    orc.trace(rays, tr, stop, run)
+    h.range_phi()
+    orc.range_phi(rays)
+    if stopk == A.STOP_THETALIM:
+        h.redshift(-1.0)
+        orc.redshift(rays, tr, -1.0)
+    else:
+        h.redshift_dest(stop)
+        orc.redshift_dest(rays, tr, stop)
+    assert_bit_identical(rays, h.rays())
+
+
+@needs_ref
+def test_live_reference_redshift_variants_and_reentrancy(orc):
+    ref = ob.Ref()
+    src = ob.make_pointsource([0, 5, 1e-3, 0], 0.2, 0.2, V=1 / (SPIN + 5 ** 1.5))
+    tr = orc.tracer(SPIN, A.TOL)
+    h = ref.pointsource(src, SPIN)
+    rays = orc.pointsource_rays(tr, src)
+    # V == -1 in redshift_start: the by-value V is overwritten by ray 0 (raytracer.cpp:391-394)
+    h.redshift_start_V(-1.0, False, True)
+    orc.redshift_start(rays, tr, -1.0, False, True)
+    assert_bit_identical(rays, h.rays(), skip=("redshift",))
+    # two passes with a small step limit: steps accumulate, stuck rays are flagged negative (raytracer.cpp:965-967)
+    stop = ob.make_stop()
+    for steplim in (200, 1000):
+        run = ob.make_run(A.RK4, steplim=steplim)
+        h.run(stop, run)
+        orc.trace(rays, tr, stop, run)
+        assert_bit_identical(rays, h.rays(), skip=("redshift",))
+    assert (rays["steps"] < -1).any()
+    for V, rev, pj, mo in [(-1.0, False, True, 0), (0.05, False, False, 0), (-0.3, False, False, 1), (0.2, True, False, 1)]:
+        h.redshift(V, rev, pj, mo)
+        orc.redshift(rays, tr, V, rev, pj, mo)
+        assert_bit_identical(rays, h.rays())
+    h.calculate_momentum()
+    orc.calculate_momentum(rays, tr)
+    assert_bit_identical(rays, h.rays())
+
+
+@needs_ref
+@pytest.mark.parametrize("tl", [-0.3, 0.0])
+@pytest.mark.parametrize("integ", [A.RK4, A.RK45])
+def test_live_reference_negative_and_zero_thetalim(orc, tl, integ):
+    ref = ob.Ref()
+    src = ob.make_pointsource([0, 8, 1.2, 0], 0.2, 0.2)
+    tr = orc.tracer(SPIN, A.TOL)
+    h = ref.pointsource(src, SPIN)
+    rays = orc.pointsource_rays(tr, src)
+    h.redshift_start()
+    orc.redshift_start(rays, tr, 0.0)
+    stop = ob.make_stop(A.STOP_THETALIM, theta_lim=tl)
+    run = ob.make_run(integ, r_max=200.0, steplim=20000)
+    h.run(stop, run)
+    orc.trace(rays, tr, stop, run)
+    assert_bit_identical(rays, h.rays(), skip=("redshift",))
+
+
+@needs_ref
+@pytest.mark.parametrize("bundles", [False, True])
+def test_live_reference_image_plane(orc, bundles):
+    ref = ob.Ref()
+    ip = ob.make_imageplane(1000.0, 30.0, -20, 20, 32, bundles=bundles)
+    tr = orc.tracer(-SPIN, A.PRECISION)
+    h = ref.imageplane(ip, SPIN)
+    rays = orc.imageplane_rays(tr, ip)
+    rr = h.rays(copy=False)
+    rr["rdot_flips"][:] = 0            # uninitialised in the reference
+    rr["equatorial_crossings"][:] = 0
+    h.redshift_start()
+    orc.redshift_start(rays, tr, 0.0, True)
+    assert_bit_identical(rays, h.rays(), skip=("redshift",))
+    stop = ob.make_stop()
+    run = ob.make_run(A.RK4, r_max=1100.0)
+    h.run(stop, run)
+    orc.trace(rays, tr, stop, run)
+    h.redshift(-1.0, True)
+    orc.redshift(rays, tr, -1.0, True)
+    h.range_phi()
+    orc.range_phi(rays)
+    assert_bit_identical(rays, h.rays())
+    if not bundles:
+        assert np.isnan(rays["r"]).sum() == 1     # the exact-centre pixel (b = 0 -> asin(0/0)), SURVEY 8c
+
+
+def test_rk45_nan_ray_is_retired_not_hung(orc):
+    """The reference spins forever on the NaN centre pixel under RK45; the oracle and the CUDA path
+    retire the ray with STEPLIM set and a negated step count instead."""
+    ip = ob.make_imageplane(1000.0, 30.0, -20, 20, 8)     # 9x9 grid containing x = y = 0 exactly
+    tr = orc.tracer(-SPIN, A.PRECISION)
+    rays = orc.imageplane_rays(tr, ip)
+    orc.redshift_start(rays, tr, 0.0, True)
+    centre = np.flatnonzero((rays["alpha"] == 0) & (rays["beta"] == 0))
+    assert len(centre) == 1 and np.isnan(rays["h"][centre[0]])
+    orc.trace(rays, tr, ob.make_stop(), ob.make_run(A.RK45, r_max=1100.0))
+    c = rays[centre[0]]
+    assert c["status"] & A.STATUS_STEPLIM and c["steps"] < 0
+    others = np.delete(np.arange(len(rays)), centre)
+    assert (rays["steps"][others] > 0).all()
