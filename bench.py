@@ -222,7 +222,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     ctx = K.get_context(local_rank)
-    stream = torch.cuda.current_stream()
+    # everything (torch fills, our kernels, NCCL) is ordered on ONE explicit stream, and the CUDA events that
+    # time the kernels are recorded on that same stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     math_mode = A.MATH_FAST if args.math == "fast" else A.MATH_EXACT
 

@@ -54,8 +54,13 @@ class Context:
             pass
 
     def set_stream(self, cuda_stream):
-        """Issue all work on an existing CUDA stream (pass torch.cuda.current_stream().cuda_stream)."""
-        check(self.L.kt_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
+        """Issue all work on an existing CUDA stream (pass torch.cuda.current_stream().cuda_stream).
+        0 means the legacy default stream (what torch uses unless told otherwise), None the context's own stream."""
+        if cuda_stream is None:
+            handle = None
+        else:
+            handle = C.c_void_p(cuda_stream if cuda_stream else 1)   # cudaStreamLegacy == (cudaStream_t)0x1
+        check(self.L.kt_set_stream(self.h, handle))
 
     def synchronize(self):
         check(self.L.kt_synchronize(self.h))
