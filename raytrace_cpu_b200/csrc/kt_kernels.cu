@@ -528,7 +528,8 @@ static cudaError_t launch_trace(const LaunchCfg& cfg, const TraceParams& P, IO i
 {
     auto kern = trace_persistent<INTEG, IO, TRACE_THREADS, MINB>;
     constexpr int WARPS = TRACE_THREADS / 32;
-    const size_t smem = (sizeof(Stage<IO::ND_IN, IO::NI_IN>) + sizeof(Stage<IO::ND_OUT, IO::NI_OUT>)) * WARPS + extra_smem;
+    const size_t smem = (sizeof(Stage<IO::ND_IN, IO::NI_IN>) + sizeof(Stage<IO::ND_OUT, IO::NI_OUT>) +
+                         KT_NCOUNTERS * sizeof(unsigned long long)) * WARPS + extra_smem;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -552,8 +553,9 @@ static cudaError_t launch_trace_any(const LaunchCfg& cfg, const TraceParams& P, 
         return launch_trace<KT_RK45, IO, 3>(cfg, P, io, extra_smem);
     }
     if (minb == 3) return launch_trace<KT_RK4, IO, 3>(cfg, P, io, extra_smem);
-    if (minb == 5) return launch_trace<KT_RK4, IO, 5>(cfg, P, io, extra_smem);
-    return launch_trace<KT_RK4, IO, 4>(cfg, P, io, extra_smem);
+    if (minb == 4) return launch_trace<KT_RK4, IO, 4>(cfg, P, io, extra_smem);
+    if (minb == 6) return launch_trace<KT_RK4, IO, 6>(cfg, P, io, extra_smem);
+    return launch_trace<KT_RK4, IO, 5>(cfg, P, io, extra_smem);   // measured best: 20 warps per SM (96 registers)
 }
 
 static inline unsigned nblocks(long long n, int t) { return (unsigned)((n + t - 1) / t); }
