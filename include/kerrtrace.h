@@ -214,6 +214,8 @@ int kt_sm_count(kt_ctx*);
 int64_t kt_kernel_launches(kt_ctx*);    /* number of kernels this ctx has launched so far */
 /* DFMA micro-benchmark: measured FP64 FMA peak in TFLOP/s (2 flop per FMA) -- the roofline denominator. */
 int kt_fp64_peak(kt_ctx*, double* tflops);
+/* dependent-issue latency of one DFMA in SM cycles (one warp, serial chain): explains the latency-bound regime */
+int kt_fp64_latency(kt_ctx*, double* cycles_per_op);
 /* tuning: resident 128-thread CTAs per SM the trace kernel is built for (3, 4 or 5; 0 = default).  Also
  * read from the environment variable KT_MIN_BLOCKS at kt_create(). */
 int kt_set_min_blocks(kt_ctx*, int min_blocks);

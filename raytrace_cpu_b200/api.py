@@ -83,6 +83,11 @@ class Context:
     def check_aborted(self):
         check(self.L.kt_aborted(self.h))
 
+    def fp64_latency_cycles(self):
+        v = C.c_double()
+        check(self.L.kt_fp64_latency(self.h, C.byref(v)))
+        return v.value
+
     def fp64_peak_tflops(self):
         v = C.c_double()
         check(self.L.kt_fp64_peak(self.h, C.byref(v)))

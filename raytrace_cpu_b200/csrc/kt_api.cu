@@ -865,6 +865,20 @@ extern "C" int kt_fp64_peak(kt_ctx* c, double* tflops)
     return KT_OK;
 }
 
+// dependent-issue latency of one DFMA in SM cycles (a single warp running a serial chain): developer diagnostic
+extern "C" int kt_fp64_latency(kt_ctx* c, double* cycles_per_op)
+{
+    if (int rc = ctx_bind(c)) return rc;
+    if (!cycles_per_op) return fail(KT_ERR_INVALID, "null output");
+    KT_CUDA(kt_kernel_table_fast()->dfma_peak(cfg_of(c), c->d_scratch, -1, 32, 4096));
+    c->launches++;
+    double h[3];
+    KT_CUDA(cudaMemcpyAsync(h, c->d_scratch, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    *cycles_per_op = h[0] / h[1];
+    return KT_OK;
+}
+
 // sizeof() of every POD struct of the ABI, so bindings can check their mirrors (tests/test_abi.py)
 extern "C" int kt_abi_sizeof(const char* name)
 {

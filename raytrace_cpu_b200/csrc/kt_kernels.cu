@@ -1,5 +1,7 @@
 // kt_kernels.cu -- IO policies, kernel instantiations and launchers.  Compiled once per arithmetic mode
 // (Makefile: -DKT_FAST=0 -fmad=false  ->  kt_kernels_exact.o ;  -DKT_FAST=1 -fmad=true  ->  kt_kernels_fast.o).
+#include <type_traits>
+
 #include "kt_kernels.h"
 #include "kt_trace.cuh"
 
@@ -518,6 +520,20 @@ __global__ void k_dfma_peak(double* out, int iters)
     if (s == 12345.678) out[0] = s;
 }
 
+// dependent-chain latency of DFMA (cycles per op for one warp alone): out[0] = cycles, out[1] = ops
+__global__ void k_dfma_latency(double* out, int iters)
+{
+    double a = threadIdx.x * 1e-9;
+    const double b = 1.0000001, c = 1e-7;
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 32; u++) a = fma(a, b, c);
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) { out[0] = (double)(t1 - t0); out[1] = (double)iters * 32.0; out[2] = a; }
+}
+
 // =========================================================================================================
 // Launchers
 // =========================================================================================================
@@ -555,6 +571,10 @@ static cudaError_t launch_trace_any(const LaunchCfg& cfg, const TraceParams& P, 
     if (minb == 3) return launch_trace<KT_RK4, IO, 3>(cfg, P, io, extra_smem);
     if (minb == 4) return launch_trace<KT_RK4, IO, 4>(cfg, P, io, extra_smem);
     if (minb == 6) return launch_trace<KT_RK4, IO, 6>(cfg, P, io, extra_smem);
+    if constexpr (std::is_same<IO, EmisIO>::value) {   // occupancy experiments on the headline kernel only
+        if (minb == 7) return launch_trace<KT_RK4, IO, 7>(cfg, P, io, extra_smem);
+        if (minb == 8) return launch_trace<KT_RK4, IO, 8>(cfg, P, io, extra_smem);
+    }
     return launch_trace<KT_RK4, IO, 5>(cfg, P, io, extra_smem);   // measured best: 20 warps per SM (96 registers)
 }
 
@@ -645,6 +665,10 @@ static cudaError_t l_bin_image(const LaunchCfg& cfg, const kt_ray* rays, long lo
 }
 static cudaError_t l_dfma_peak(const LaunchCfg& cfg, double* out, int blocks, int threads, int iters)
 {
+    if (blocks < 0) {   // latency mode: one warp, dependent chain
+        k_dfma_latency<<<1, 32, 0, cfg.stream>>>(out, iters);
+        return cudaGetLastError();
+    }
     k_dfma_peak<<<blocks, threads, 0, cfg.stream>>>(out, iters);
     return cudaGetLastError();
 }

@@ -25,6 +25,7 @@ args = ap.parse_args()
 
 ctx = K.get_context(0)
 ctx.set_timeout(600.0)
+print(f"DFMA dependent latency: {ctx.fp64_latency_cycles():.2f} cycles/op", flush=True)
 if args.min_blocks:
     ctx.set_min_blocks(args.min_blocks)
 dcos, dbeta, _ = bench.grid_for(int(args.rays), n_beta=max(100, int(round(args.rays ** 0.5))))
