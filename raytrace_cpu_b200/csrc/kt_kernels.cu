@@ -575,7 +575,14 @@ static cudaError_t launch_trace_any(const LaunchCfg& cfg, const TraceParams& P, 
         if (minb == 7) return launch_trace<KT_RK4, IO, 7>(cfg, P, io, extra_smem);
         if (minb == 8) return launch_trace<KT_RK4, IO, 8>(cfg, P, io, extra_smem);
     }
-    return launch_trace<KT_RK4, IO, 5>(cfg, P, io, extra_smem);   // measured best: 20 warps per SM (96 registers)
+    // default = measured best on B200 (15e6-ray lamppost runs, profiles/README.md): the kernel is bound by FP64
+    // dependency latency (DFMA: 8 cycles), so resident warps beat spill-free registers --
+    //   exact: 4/5/6/7/8 CTAs per SM -> 2.68 / 2.91 / 3.04 / 2.99 / 2.43 e7 rays/s ; fast: 4.37 / 4.67 / 4.67 / 4.56 / 4.61 e7
+#if KT_FAST
+    return launch_trace<KT_RK4, IO, 5>(cfg, P, io, extra_smem);
+#else
+    return launch_trace<KT_RK4, IO, 6>(cfg, P, io, extra_smem);
+#endif
 }
 
 static inline unsigned nblocks(long long n, int t) { return (unsigned)((n + t - 1) / t); }

@@ -1,0 +1,27 @@
+#!/bin/sh
+# Builds the reference's own, UNMODIFIED application sources against the kerrtrace shim:
+# an overlay tree is made of symlinks into the reference checkout with src/raytracer/ replaced by the shim
+# headers; nothing is copied.  Usage: build_apps.sh [reference-root] [output-dir]
+set -e
+HERE=$(cd "$(dirname "$0")" && pwd)
+REPO=$(cd "$HERE/../.." && pwd)
+REF=${1:-/root/reference}
+OUT=${2:-$HERE/_built}
+CXX=/usr/bin/g++; [ -x "$CXX" ] || CXX=g++
+OVL=$(mktemp -d)
+trap 'rm -rf "$OVL"' EXIT
+mkdir -p "$OVL/src" "$OUT"
+# real directories holding per-file symlinks, so that the sources' relative includes ("../raytracer/...",
+# "../include/...") resolve inside the overlay and not through the physical parent of a symlinked directory
+ln -s "$REF/src/include" "$OVL/src/include"
+for d in emissivity imageplane caustic tests; do
+    mkdir "$OVL/src/$d"
+    ln -s "$REF/src/$d"/*.cpp "$OVL/src/$d/"
+done
+mkdir "$OVL/src/raytracer"
+ln -s "$HERE/raytracer"/*.h "$OVL/src/raytracer/"
+FLAGS="-O2 -fopenmp -w -I$OVL/src -I$REPO/include -L$REPO/raytrace_cpu_b200 -Wl,-rpath,$REPO/raytrace_cpu_b200"
+$CXX $FLAGS "$OVL/src/emissivity/emissivity_rd.cpp" -o "$OUT/emissivity_rd" -lkerrtrace
+$CXX $FLAGS "$OVL/src/tests/emissivity_rk45_test.cpp" -o "$OUT/emissivity_rk45_test" -lkerrtrace
+$CXX $FLAGS "$OVL/src/tests/integrator_perf_test.cpp" -o "$OUT/integrator_perf_test" -lkerrtrace
+echo "built: $(ls "$OUT")"

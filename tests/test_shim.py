@@ -1,0 +1,116 @@
+"""The drop-in boundary from the application side: the reference's own, UNMODIFIED application and test sources are
+compiled against the source-compatible shim headers (raytrace_cpu_b200/shim/raytracer/) and linked to libkerrtrace.so.
+
+* CPU: every application of the three families in scope compiles (the FITS writers against a declarations-only
+  fitsio.h, cfitsio being absent here); the ones that link without cfitsio are built into shim/_built/.
+  These need the reference checkout and are skipped where /root/reference does not exist.
+* GPU: the prebuilt binaries (they travel with the repo snapshot) are RUN on the B200: the reference's
+  emissivity_rd application reproduces the 7-column profile its CPU build wrote (tests/golden/emissivity_rd_app.dat),
+  and the reference's own acceptance test emissivity_rk45_test prints PASS.
+"""
+import os
+import shutil
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "raytrace_cpu_b200", "shim")
+BUILT = os.path.join(SHIM, "_built")
+REF = "/root/reference"
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+needs_reference = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "raytracer")), reason="reference checkout absent")
+
+
+def make_overlay(tmp):
+    src = os.path.join(tmp, "src")
+    os.makedirs(src)
+    os.symlink(os.path.join(REF, "src", "include"), os.path.join(src, "include"))
+    for d in ("emissivity", "imageplane", "caustic", "tests"):
+        os.makedirs(os.path.join(src, d))
+        for f in os.listdir(os.path.join(REF, "src", d)):
+            if f.endswith(".cpp"):
+                os.symlink(os.path.join(REF, "src", d, f), os.path.join(src, d, f))
+    os.makedirs(os.path.join(src, "raytracer"))
+    for f in os.listdir(os.path.join(SHIM, "raytracer")):
+        os.symlink(os.path.join(SHIM, "raytracer", f), os.path.join(src, "raytracer", f))
+    return src
+
+
+@needs_reference
+@pytest.mark.parametrize("app", [
+    "emissivity/emissivity_rd.cpp", "imageplane/imageplane_disc_image.cpp", "imageplane/imageplane_disc_image_rd.cpp",
+    "imageplane/imageplane_disc_image_isco.cpp", "caustic/caustic_discplane.cpp", "caustic/caustic_plane.cpp",
+    "caustic/caustic_sourceplane.cpp", "tests/emissivity_rk45_test.cpp", "tests/integrator_perf_test.cpp",
+    "tests/emissivity_rk45_plot.cpp",
+])
+def test_unmodified_reference_sources_compile_against_the_shim(app):
+    with tempfile.TemporaryDirectory() as tmp:
+        src = make_overlay(tmp)
+        cmd = ["/usr/bin/g++", "-fsyntax-only", "-fopenmp", "-w", f"-I{src}", f"-I{ROOT}/include", f"-I{ROOT}/tests/fitsio_stub",
+               os.path.join(src, app)]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr[-2000:]
+
+
+@needs_reference
+def test_build_script_links_the_apps():
+    p = subprocess.run([os.path.join(SHIM, "build_apps.sh")], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    for exe in ("emissivity_rd", "emissivity_rk45_test", "integrator_perf_test"):
+        assert os.access(os.path.join(BUILT, exe), os.X_OK)
+    deps = subprocess.run(["ldd", os.path.join(BUILT, "emissivity_rd")], capture_output=True, text=True).stdout
+    assert "libkerrtrace.so" in deps
+
+
+def test_shim_headers_do_not_copy_the_reference_engine():
+    """The shim holds interface declarations and calls into the C ABI -- no integrator."""
+    for f in os.listdir(os.path.join(SHIM, "raytracer")):
+        text = open(os.path.join(SHIM, "raytracer", f)).read()
+        assert "momentum_from_consts<T>(pt2" not in text and "a21" not in text
+    assert "kt_trace(" in open(os.path.join(SHIM, "raytracer", "raytracer.h")).read()
+
+
+built = pytest.mark.skipif(not os.path.exists(os.path.join(BUILT, "emissivity_rd")), reason="shim/_built not present")
+
+
+@pytest.mark.gpu
+@built
+def test_reference_emissivity_rd_app_runs_unchanged_on_the_gpu():
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "par"))
+        os.makedirs(os.path.join(tmp, "bin"))
+        out = os.path.join(tmp, "out.dat")
+        with open(os.path.join(tmp, "par", "emissivity_rd.par"), "w") as f:
+            f.write(f"outfile = {out}\ntheta_lim = 1.5707963\nsource = 0 10 1E-3 1.5707\nV = 0\nspin = 0.998\n"
+                    "dcosalpha = 0.02\ndbeta = 0.02\nNr = 30\nlogbin_r = 1\nshow_progress = 0\n")
+        env = dict(os.environ, KERRTRACE_QUIET="1")
+        p = subprocess.run([os.path.join(BUILT, "emissivity_rd")], cwd=os.path.join(tmp, "bin"), capture_output=True, text=True,
+                           env=env, timeout=300)
+        assert p.returncode == 0, p.stdout + p.stderr
+        got = np.genfromtxt(out)
+    want = np.genfromtxt(os.path.join(GOLDEN, "emissivity_rd_app.dat"))      # written by the reference's CPU build
+    assert got.shape == want.shape == (30, 7)
+    np.testing.assert_allclose(got[:, 0], want[:, 0], rtol=1e-8)              # bin radii
+    np.testing.assert_allclose(got[:, 1], want[:, 1], rtol=1e-8)              # proper areas (host code of the app)
+    assert np.abs(got[:, 2] - want[:, 2]).sum() <= 0.002 * want[:, 2].sum()   # rays per annulus
+    same = (got[:, 2] == want[:, 2]) & (want[:, 2] >= 100)
+    assert same.sum() >= 5
+    for col in (3, 4, 5, 6):                                                 # flux, emissivity, <g>, <t>
+        np.testing.assert_allclose(got[same, col], want[same, col], rtol=2e-3)
+        assert (np.abs(got[same, col] / want[same, col] - 1) <= 2e-8).mean() >= 0.8
+
+
+@pytest.mark.gpu
+@built
+def test_reference_acceptance_test_passes_on_the_gpu():
+    """src/tests/emissivity_rk45_test.cpp (RK4 vs RK45 binned profiles), built unchanged."""
+    env = dict(os.environ, KERRTRACE_QUIET="1")
+    p = subprocess.run([os.path.join(BUILT, "emissivity_rk45_test")], capture_output=True, text=True, env=env, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert "PASS" in p.stdout
+    p = subprocess.run([os.path.join(BUILT, "integrator_perf_test")], capture_output=True, text=True, env=env, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
