@@ -106,10 +106,14 @@ def cpu_reference_run(n_rays, end_to_end=False):
 
     dcos, dbeta, _ = grid_for(n_rays, n_beta=max(100, int(round(math.sqrt(n_rays)))))
     src = ob.make_pointsource(SOURCE, dcos, dbeta, cosalpha0=COS0, cosalphamax=COSMAX, beta0=BETA0, betamax=BETAMAX)
-    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     if ob.ref_available():
         kind = "reference"
         ref = ob.Ref()
+        cores = ref.set_num_threads(cores)      # torchrun exports OMP_NUM_THREADS=1: use every host thread anyway
         t_all0 = time.perf_counter()
         h = ref.pointsource(src, SPIN, A.TOL)
         h.redshift_start()
@@ -129,7 +133,7 @@ def cpu_reference_run(n_rays, end_to_end=False):
         rays = orc.pointsource_rays(tr, src)
         orc.redshift_start(rays, tr, 0.0)
         t0 = time.perf_counter()
-        orc.trace(rays, tr, ob.make_stop(), ob.make_run(A.RK4))
+        orc.trace(rays, tr, ob.make_stop(), ob.make_run(A.RK4), cores)
         secs = time.perf_counter() - t0
         orc.range_phi(rays)
         orc.redshift(rays, tr, -1.0)

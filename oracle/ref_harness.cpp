@@ -14,6 +14,8 @@
 //   kerr_horizon / kerr_isco / integrate_disc_area     kerr.h:13-32, disc.h:125-141
 //
 // Nothing here re-implements any arithmetic: every call forwards to the reference object.
+#include <omp.h>
+
 #include <chrono>
 #include <cstdint>
 #include <cstring>
@@ -66,6 +68,11 @@ Integrator to_integrator(int m) {
 extern "C" {
 
 int ref_sizeof_ray() { return (int)sizeof(Ray<double>); }
+
+// OpenMP team size of the reference's parallel loop (torchrun exports OMP_NUM_THREADS=1; the CPU baseline must
+// use every host thread it can)
+void ref_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int ref_max_threads() { return omp_get_max_threads(); }
 
 void* ref_pointsource_create(const double* pos, double V, double spin, double tol, double dcosalpha, double dbeta,
                              double cosalpha0, double cosalphamax, double beta0, double betamax, double E) {

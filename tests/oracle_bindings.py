@@ -189,6 +189,8 @@ class Ref:
         L = self.L = C.CDLL(path)
         d = C.c_double
         L.ref_sizeof_ray.restype = C.c_int
+        L.ref_set_num_threads.argtypes = [C.c_int]
+        L.ref_max_threads.restype = C.c_int
         L.ref_pointsource_create.restype = C.c_void_p
         L.ref_pointsource_create.argtypes = [A.c_double_p] + [d] * 10
         L.ref_imageplane_create.restype = C.c_void_p
@@ -239,6 +241,10 @@ class Ref:
             h = self.L.ref_imageplane_create(ip.dist, ip.incl_deg, ip.x0, ip.xmax, ip.dx, ip.y0, ip.ymax, ip.dy, spin,
                                              ip.phi0, precision)
         return RefSource(self.L, h)
+
+    def set_num_threads(self, n):
+        self.L.ref_set_num_threads(int(n))
+        return self.L.ref_max_threads()
 
     def kerr_isco(self, a, sign=+1):
         return self.L.ref_kerr_isco(a, sign)
