@@ -57,6 +57,14 @@ struct kt_ctx {
     long long launches = 0;
     int min_blocks = 0;
     double timeout_s = 0;              // watchdog for the persistent kernels (0 = off)
+    // chunk pipeline of the host-buffer trace: 3 streams, each with its own work queue and statistics block
+    static const int NPIPE = 3;
+    cudaStream_t pipe[NPIPE] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_done[NPIPE] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_start = nullptr;
+    unsigned long long* d_pipe_queue = nullptr;   // NPIPE counters
+    double* d_pipe_cnt = nullptr;                 // NPIPE x KT_NCOUNTERS
+    long long pipe_chunk = 1 << 21;               // rays per chunk (302 MB of kt_ray)
 };
 
 struct kt_rayset {
@@ -156,6 +164,19 @@ extern "C" kt_ctx* kt_create(int device)
     c->min_blocks = mb ? atoi(mb) : 0;
     const char* to = getenv("KT_TIMEOUT_S");
     c->timeout_s = to ? atof(to) : 0;
+    const char* pc = getenv("KT_PIPE_CHUNK");
+    if (pc && atoll(pc) > 0) c->pipe_chunk = atoll(pc);
+    bool pipe_ok = cudaEventCreateWithFlags(&c->pipe_start, cudaEventDisableTiming) == cudaSuccess &&
+                   cudaMalloc(&c->d_pipe_queue, kt_ctx::NPIPE * sizeof(unsigned long long)) == cudaSuccess &&
+                   cudaMalloc(&c->d_pipe_cnt, kt_ctx::NPIPE * KT_NCOUNTERS * sizeof(double)) == cudaSuccess;
+    for (int i = 0; i < kt_ctx::NPIPE && pipe_ok; i++)
+        pipe_ok = cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&c->pipe_done[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!pipe_ok) {
+        fail(KT_ERR_CUDA, "context creation failed (pipeline streams): %s", cudaGetErrorString(cudaGetLastError()));
+        kt_destroy(c);
+        return nullptr;
+    }
     if (ensure_scratch(c, 1 << 20) != KT_OK || ensure_pinned(c, 1 << 20) != KT_OK) {
         kt_destroy(c);
         return nullptr;
@@ -172,6 +193,13 @@ extern "C" void kt_destroy(kt_ctx* c)
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->d_rays) cudaFree(c->d_rays);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    for (int i = 0; i < kt_ctx::NPIPE; i++) {
+        if (c->pipe[i]) cudaStreamDestroy(c->pipe[i]);
+        if (c->pipe_done[i]) cudaEventDestroy(c->pipe_done[i]);
+    }
+    if (c->pipe_start) cudaEventDestroy(c->pipe_start);
+    if (c->d_pipe_queue) cudaFree(c->d_pipe_queue);
+    if (c->d_pipe_cnt) cudaFree(c->d_pipe_cnt);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -693,11 +721,45 @@ static int stage_out(kt_ctx* c, kt_ray* rays, int64_t n)
     return c->timeout_s > 0 ? kt_aborted(c) : KT_OK;
 }
 
+// run_raytrace on a HOST ray array.  The array is cut into chunks that flow through three streams
+// (H2D copy -> persistent trace kernel -> D2H copy per chunk): the copies of one chunk overlap the kernels of its
+// neighbours, and the few long rays that keep a finished chunk's kernel alive overlap the next chunk's bulk
+// (CTAs of the next kernel are scheduled as soon as CTAs of the previous one exit).
 extern "C" int kt_trace(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, const kt_run* run, kt_ray* rays, int64_t n)
 {
-    if (int rc = stage_in(c, rays, n, true)) return rc;
-    if (int rc = dev_trace(c, c->d_rays, n, tr, stop, run)) return rc;
-    return stage_out(c, rays, n);
+    if (!stop || !run) return fail(KT_ERR_INVALID, "null stop / run");
+    if (int rc = stage_in(c, rays, n, false)) return rc;
+    if (n == 0) return KT_OK;
+    TraceParams P0;
+    if (int rc = make_params(P0, tr, stop, run)) return rc;
+    const KernelTable* T = table_for(run->math_mode);
+    KT_CUDA(cudaEventRecord(c->pipe_start, c->stream));
+    for (int i = 0; i < kt_ctx::NPIPE; i++) KT_CUDA(cudaStreamWaitEvent(c->pipe[i], c->pipe_start, 0));
+    KT_CUDA(cudaMemsetAsync(c->d_pipe_cnt, 0, kt_ctx::NPIPE * KT_NCOUNTERS * sizeof(double), c->pipe[0]));
+    const long long chunk = c->pipe_chunk;
+    int k = 0;
+    for (long long off = 0; off < n; off += chunk, k++) {
+        const long long len = (n - off < chunk) ? (n - off) : chunk;
+        const int si = k % kt_ctx::NPIPE;
+        cudaStream_t st = c->pipe[si];
+        kt_ray* d = c->d_rays + off;
+        KT_CUDA(cudaMemcpyAsync(d, rays + off, (size_t)len * sizeof(kt_ray), cudaMemcpyHostToDevice, st));
+        TraceParams P = P0;
+        set_work(P, c, len, nullptr);
+        P.queue = c->d_pipe_queue + si;
+        KT_CUDA(cudaMemsetAsync(P.queue, 0, sizeof(unsigned long long), st));
+        LaunchCfg cfg = cfg_of(c);
+        cfg.stream = st;
+        KT_CUDA(T->trace_rayset(cfg, P, d, c->d_pipe_cnt + si * KT_NCOUNTERS));
+        c->launches++;
+        KT_CUDA(cudaMemcpyAsync(rays + off, d, (size_t)len * sizeof(kt_ray), cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < kt_ctx::NPIPE; i++) {
+        KT_CUDA(cudaEventRecord(c->pipe_done[i], c->pipe[i]));
+        KT_CUDA(cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0));
+    }
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    return c->timeout_s > 0 ? kt_aborted(c) : KT_OK;
 }
 extern "C" int kt_redshift_start(kt_ctx* c, const kt_tracer* tr, kt_ray* rays, int64_t n, double V, int reverse, int projradius)
 {
