@@ -57,14 +57,14 @@ struct kt_ctx {
     long long launches = 0;
     int min_blocks = 0;
     double timeout_s = 0;              // watchdog for the persistent kernels (0 = off)
-    // chunk pipeline of the host-buffer trace: 3 streams, each with its own work queue and statistics block
-    static const int NPIPE = 3;
-    cudaStream_t pipe[NPIPE] = {nullptr, nullptr, nullptr};
-    cudaEvent_t pipe_done[NPIPE] = {nullptr, nullptr, nullptr};
+    // chunk pipeline of the host-buffer trace: 4 streams, each with its own work queue and statistics block
+    static const int NPIPE = 4;
+    cudaStream_t pipe[NPIPE] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_done[NPIPE] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t pipe_start = nullptr;
     unsigned long long* d_pipe_queue = nullptr;   // NPIPE counters
     double* d_pipe_cnt = nullptr;                 // NPIPE x KT_NCOUNTERS
-    long long pipe_chunk = 1 << 21;               // rays per chunk (302 MB of kt_ray)
+    long long pipe_chunk = 1 << 20;               // smallest chunk worth its own kernel launch (151 MB of kt_ray)
 };
 
 struct kt_rayset {
@@ -721,10 +721,12 @@ static int stage_out(kt_ctx* c, kt_ray* rays, int64_t n)
     return c->timeout_s > 0 ? kt_aborted(c) : KT_OK;
 }
 
-// run_raytrace on a HOST ray array.  The array is cut into chunks that flow through three streams
-// (H2D copy -> persistent trace kernel -> D2H copy per chunk): the copies of one chunk overlap the kernels of its
-// neighbours, and the few long rays that keep a finished chunk's kernel alive overlap the next chunk's bulk
-// (CTAs of the next kernel are scheduled as soon as CTAs of the previous one exit).
+// run_raytrace on a HOST ray array.  The array is cut into at most NPIPE chunks, each on its own stream
+// (H2D copy -> persistent trace kernel -> D2H copy): the copies of one chunk overlap the kernels of its neighbours,
+// and the few long rays that keep a finished chunk's kernel alive overlap the next chunk's bulk (CTAs of the next
+// kernel are scheduled as soon as CTAs of the previous one exit).  A stream is never reused within a call:
+// measured on B200, a second chunk queued behind a kernel's straggling rays (which step ~2.5x slower while the
+// SMs are full) stalls the whole pipeline.
 extern "C" int kt_trace(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, const kt_run* run, kt_ray* rays, int64_t n)
 {
     if (!stop || !run) return fail(KT_ERR_INVALID, "null stop / run");
@@ -736,7 +738,9 @@ extern "C" int kt_trace(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, con
     KT_CUDA(cudaEventRecord(c->pipe_start, c->stream));
     for (int i = 0; i < kt_ctx::NPIPE; i++) KT_CUDA(cudaStreamWaitEvent(c->pipe[i], c->pipe_start, 0));
     KT_CUDA(cudaMemsetAsync(c->d_pipe_cnt, 0, kt_ctx::NPIPE * KT_NCOUNTERS * sizeof(double), c->pipe[0]));
-    const long long chunk = c->pipe_chunk;
+    long long nchunks = n / c->pipe_chunk;
+    nchunks = nchunks < 1 ? 1 : (nchunks > kt_ctx::NPIPE ? kt_ctx::NPIPE : nchunks);
+    const long long chunk = ((n + nchunks - 1) / nchunks + 31) / 32 * 32;
     int k = 0;
     for (long long off = 0; off < n; off += chunk, k++) {
         const long long len = (n - off < chunk) ? (n - off) : chunk;
