@@ -718,6 +718,15 @@ static int stage_out(kt_ctx* c, kt_ray* rays, int64_t n)
     if (n == 0) return KT_OK;
     KT_CUDA(cudaMemcpyAsync(rays, c->d_rays, (size_t)n * sizeof(kt_ray), cudaMemcpyDeviceToHost, c->stream));
     KT_CUDA(cudaStreamSynchronize(c->stream));
+    if (trace_pipe) {
+        for (int i = 0; i < k && i < kt_ctx::NPIPE; i++) {
+            float t[4];
+            for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], ev[0][0], ev[i][j]);
+            fprintf(stderr, "kt_trace chunk %d: H2D %.1f-%.1f ms, kernel done %.1f ms, D2H done %.1f ms\n", i, t[0], t[1], t[2], t[3]);
+        }
+        for (int i = 0; i < kt_ctx::NPIPE; i++)
+            for (int j = 0; j < 4; j++) cudaEventDestroy(ev[i][j]);
+    }
     return c->timeout_s > 0 ? kt_aborted(c) : KT_OK;
 }
 
@@ -740,6 +749,11 @@ extern "C" int kt_trace(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, con
     KT_CUDA(cudaMemsetAsync(c->d_pipe_cnt, 0, kt_ctx::NPIPE * KT_NCOUNTERS * sizeof(double), c->pipe[0]));
     long long nchunks = n / c->pipe_chunk;
     nchunks = nchunks < 1 ? 1 : (nchunks > kt_ctx::NPIPE ? kt_ctx::NPIPE : nchunks);
+    const bool trace_pipe = getenv("KT_PIPE_TRACE") != nullptr;   // developer aid: print the per-chunk timeline
+    cudaEvent_t ev[kt_ctx::NPIPE][4];
+    if (trace_pipe)
+        for (int i = 0; i < kt_ctx::NPIPE; i++)
+            for (int j = 0; j < 4; j++) cudaEventCreate(&ev[i][j]);
     const long long chunk = ((n + nchunks - 1) / nchunks + 31) / 32 * 32;
     int k = 0;
     for (long long off = 0; off < n; off += chunk, k++) {
@@ -747,7 +761,9 @@ extern "C" int kt_trace(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, con
         const int si = k % kt_ctx::NPIPE;
         cudaStream_t st = c->pipe[si];
         kt_ray* d = c->d_rays + off;
+        if (trace_pipe) cudaEventRecord(ev[si][0], st);
         KT_CUDA(cudaMemcpyAsync(d, rays + off, (size_t)len * sizeof(kt_ray), cudaMemcpyHostToDevice, st));
+        if (trace_pipe) cudaEventRecord(ev[si][1], st);
         TraceParams P = P0;
         set_work(P, c, len, nullptr);
         P.queue = c->d_pipe_queue + si;
@@ -756,7 +772,9 @@ extern "C" int kt_trace(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, con
         cfg.stream = st;
         KT_CUDA(T->trace_rayset(cfg, P, d, c->d_pipe_cnt + si * KT_NCOUNTERS));
         c->launches++;
+        if (trace_pipe) cudaEventRecord(ev[si][2], st);
         KT_CUDA(cudaMemcpyAsync(rays + off, d, (size_t)len * sizeof(kt_ray), cudaMemcpyDeviceToHost, st));
+        if (trace_pipe) cudaEventRecord(ev[si][3], st);
     }
     for (int i = 0; i < kt_ctx::NPIPE; i++) {
         KT_CUDA(cudaEventRecord(c->pipe_done[i], c->pipe[i]));

@@ -566,7 +566,10 @@ static cudaError_t launch_trace_any(const LaunchCfg& cfg, const TraceParams& P, 
 {
     const int minb = cfg.min_blocks;
     if (P.integrator == KT_RK45) {
-        return launch_trace<KT_RK45, IO, 3>(cfg, P, io, extra_smem);
+        if (minb == 3) return launch_trace<KT_RK45, IO, 3>(cfg, P, io, extra_smem);
+        if (minb == 5) return launch_trace<KT_RK45, IO, 5>(cfg, P, io, extra_smem);
+        if (minb == 6) return launch_trace<KT_RK45, IO, 6>(cfg, P, io, extra_smem);
+        return launch_trace<KT_RK45, IO, 4>(cfg, P, io, extra_smem);
     }
     if (minb == 3) return launch_trace<KT_RK4, IO, 3>(cfg, P, io, extra_smem);
     if (minb == 4) return launch_trace<KT_RK4, IO, 4>(cfg, P, io, extra_smem);
