@@ -718,15 +718,6 @@ static int stage_out(kt_ctx* c, kt_ray* rays, int64_t n)
     if (n == 0) return KT_OK;
     KT_CUDA(cudaMemcpyAsync(rays, c->d_rays, (size_t)n * sizeof(kt_ray), cudaMemcpyDeviceToHost, c->stream));
     KT_CUDA(cudaStreamSynchronize(c->stream));
-    if (trace_pipe) {
-        for (int i = 0; i < k && i < kt_ctx::NPIPE; i++) {
-            float t[4];
-            for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], ev[0][0], ev[i][j]);
-            fprintf(stderr, "kt_trace chunk %d: H2D %.1f-%.1f ms, kernel done %.1f ms, D2H done %.1f ms\n", i, t[0], t[1], t[2], t[3]);
-        }
-        for (int i = 0; i < kt_ctx::NPIPE; i++)
-            for (int j = 0; j < 4; j++) cudaEventDestroy(ev[i][j]);
-    }
     return c->timeout_s > 0 ? kt_aborted(c) : KT_OK;
 }
 
@@ -781,6 +772,15 @@ extern "C" int kt_trace(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, con
         KT_CUDA(cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0));
     }
     KT_CUDA(cudaStreamSynchronize(c->stream));
+    if (trace_pipe) {
+        for (int i = 0; i < k && i < kt_ctx::NPIPE; i++) {
+            float t[4];
+            for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], ev[0][0], ev[i][j]);
+            fprintf(stderr, "kt_trace chunk %d: H2D %.1f-%.1f ms, kernel done %.1f ms, D2H done %.1f ms\n", i, t[0], t[1], t[2], t[3]);
+        }
+        for (int i = 0; i < kt_ctx::NPIPE; i++)
+            for (int j = 0; j < 4; j++) cudaEventDestroy(ev[i][j]);
+    }
     return c->timeout_s > 0 ? kt_aborted(c) : KT_OK;
 }
 extern "C" int kt_redshift_start(kt_ctx* c, const kt_tracer* tr, kt_ray* rays, int64_t n, double V, int reverse, int projradius)
