@@ -64,7 +64,7 @@ struct kt_ctx {
     cudaEvent_t pipe_start = nullptr;
     unsigned long long* d_pipe_queue = nullptr;   // NPIPE counters
     double* d_pipe_cnt = nullptr;                 // NPIPE x KT_NCOUNTERS
-    long long pipe_chunk = 1 << 20;               // smallest chunk worth its own kernel launch (151 MB of kt_ray)
+    long long pipe_chunk = 1ll << 40;             // rays per chunk: default = no chunking (see kt_trace); KT_PIPE_CHUNK overrides
 };
 
 struct kt_rayset {
@@ -721,12 +721,12 @@ static int stage_out(kt_ctx* c, kt_ray* rays, int64_t n)
     return c->timeout_s > 0 ? kt_aborted(c) : KT_OK;
 }
 
-// run_raytrace on a HOST ray array.  The array is cut into at most NPIPE chunks, each on its own stream
-// (H2D copy -> persistent trace kernel -> D2H copy): the copies of one chunk overlap the kernels of its neighbours,
-// and the few long rays that keep a finished chunk's kernel alive overlap the next chunk's bulk (CTAs of the next
-// kernel are scheduled as soon as CTAs of the previous one exit).  A stream is never reused within a call:
-// measured on B200, a second chunk queued behind a kernel's straggling rays (which step ~2.5x slower while the
-// SMs are full) stalls the whole pipeline.
+// run_raytrace on a HOST ray array: H2D copy -> persistent trace kernel -> D2H copy.
+// The array CAN be cut into up to NPIPE chunks, each on its own stream, so that copies overlap kernels
+// (KT_PIPE_CHUNK=<rays>), but that is off by default: measured on B200 (1.6e7 rays, profiles/README.md) the copies are
+// cheap (2.3 GB each way in 41 ms = 55 GB/s, 12 % of the call) while every chunk brings its own straggling rays
+// (the kernel of a 4e6-ray chunk lives 360 ms for 130 ms of bulk work), and chunk kernels queued behind them
+// lose more than the overlap wins: 1 chunk 711 ms, 2 chunks 765 ms, 4 chunks 886 ms.
 extern "C" int kt_trace(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, const kt_run* run, kt_ray* rays, int64_t n)
 {
     if (!stop || !run) return fail(KT_ERR_INVALID, "null stop / run");

@@ -9,7 +9,9 @@ import os
 from . import _abi as A
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkerrtrace.so")
+# KT_LIB=<variant> loads an experimental build libkerrtrace_<variant>.so (csrc/Makefile: VARIANT=...)
+_VARIANT = os.environ.get("KT_LIB", "")
+LIB_PATH = os.path.join(_HERE, f"libkerrtrace_{_VARIANT}.so" if _VARIANT else "libkerrtrace.so")
 
 
 class KerrtraceError(RuntimeError):
