@@ -24,4 +24,10 @@ FLAGS="-O2 -fopenmp -w -I$OVL/src -I$REPO/include -L$REPO/raytrace_cpu_b200 -Wl,
 $CXX $FLAGS "$OVL/src/emissivity/emissivity_rd.cpp" -o "$OUT/emissivity_rd" -lkerrtrace
 $CXX $FLAGS "$OVL/src/tests/emissivity_rk45_test.cpp" -o "$OUT/emissivity_rk45_test" -lkerrtrace
 $CXX $FLAGS "$OVL/src/tests/integrator_perf_test.cpp" -o "$OUT/integrator_perf_test" -lkerrtrace
+# the FITS-writing applications, with the bundled minimal FITS writer standing in for cfitsio (absent from this image)
+/usr/bin/gcc -O2 -c "$HERE/minifits/minifits.c" -o "$OVL/minifits.o"
+for app in imageplane/imageplane_disc_image imageplane/imageplane_disc_image_rd imageplane/imageplane_disc_image_isco \
+           caustic/caustic_discplane caustic/caustic_plane caustic/caustic_sourceplane; do
+    $CXX $FLAGS -I"$HERE/minifits" "$OVL/src/$app.cpp" "$OVL/minifits.o" -o "$OUT/$(basename $app)" -lkerrtrace
+done
 echo "built: $(ls "$OUT")"

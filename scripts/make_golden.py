@@ -22,6 +22,8 @@ from raytrace_cpu_b200 import _abi as A  # noqa: E402
 import oracle_bindings as ob  # noqa: E402
 from golden_cases import CASES, build_source  # noqa: E402
 
+from golden_cases import APP_PARS  # noqa: E402
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 REF = "/root/reference"
 
@@ -91,6 +93,25 @@ def main():
                     "dcosalpha = 0.02\ndbeta = 0.02\nNr = 30\nlogbin_r = 1\nshow_progress = 0\n")
         subprocess.run([exe], check=True, stdout=subprocess.DEVNULL, cwd=os.path.join(tmp, "bin"))
         print("emissivity_rd_app.dat:", sum(1 for _ in open(out)), "lines")
+
+        # the reference's FITS-writing applications (CPU build of the reference, linked with the bundled minimal
+        # FITS writer because cfitsio is not installed here): golden multi-extension FITS files
+        minifits = os.path.join(ROOT, "raytrace_cpu_b200", "shim", "minifits")
+        obj = os.path.join(tmp, "minifits.o")
+        subprocess.run(["/usr/bin/gcc", "-O2", "-c", os.path.join(minifits, "minifits.c"), "-o", obj], check=True)
+        for app, src_file, imp in (("imageplane_disc_image", "imageplane/imageplane_disc_image.cpp", "imageplane.cpp"),
+                                   ("caustic_discplane", "caustic/caustic_discplane.cpp", "imageplane.cpp")):
+            exe = os.path.join(tmp, app)
+            subprocess.run(["/usr/bin/g++", "-O2", "-fopenmp", "-ffp-contract=off", "-w", f"-I{REF}/src", f"-I{REF}/src/raytracer",
+                            f"-I{minifits}", f"{REF}/src/{src_file}", f"{REF}/src/raytracer/raytracer.cpp",
+                            f"{REF}/src/raytracer/{imp}", obj, "-o", exe], check=True)
+            for parname, text in APP_PARS[app].items():
+                out = os.path.join(GOLDEN, parname + ".fits")
+                par = os.path.join(tmp, parname + ".par")
+                with open(par, "w") as f:
+                    f.write(f"outfile = {out}\n" + text)
+                subprocess.run([exe, f"--parfile={par}"], check=True, stdout=subprocess.DEVNULL, cwd=os.path.join(tmp, "bin"))
+                print(parname + ".fits:", os.path.getsize(out), "bytes")
 
 
 if __name__ == "__main__":

@@ -55,3 +55,20 @@ def tracer_for(case, make_tracer):
     if "rk45_tol" in case:
         tr.rk45_tol = case["rk45_tol"]
     return tr
+
+
+# par files (minus the outfile line) of the application-level golden runs: the reference's own binaries, CPU build.
+# BASELINE config 2 / config 4 geometries at low resolution.  imageplane_disc_image must use rk4: its 49 x 49 grid holds
+# the exact-centre pixel on which the reference's RK45 never terminates.
+APP_PARS = {
+    "imageplane_disc_image": {
+        "app_image_rk4": "dist = 10000\nincl = 30\nspin = 0.998\nr_disc = 30\nx0 = -30\nxmax = 30\ny0 = -30\nymax = 30\n"
+                         "Nx = 48\nimg_Nx = 48\nq1 = 3\nrb1 = 4\nq2 = 3\nrb2 = 10\nq3 = 3\nintegrator = rk4\nshow_progress = 0\n",
+    },
+    "caustic_discplane": {
+        "app_caustic_rk4": "dist = 500\nincl = 30\nplane_phi0 = 0\nspin = 0.998\nr_disc = 50\nx0 = -20\nxmax = 20\ny0 = -20\nymax = 20\n"
+                           "Nx = 40\nNy = 40\nintegrator = rk4\nprecision = 100\nshow_progress = 0\nbundle_eps_frac = 0.01\n",
+        "app_caustic_rk45": "dist = 500\nincl = 30\nplane_phi0 = 0\nspin = 0.998\nr_disc = 50\nx0 = -20\nxmax = 20\ny0 = -20\nymax = 20\n"
+                            "Nx = 24\nNy = 24\nintegrator = rk45\nrk45_tol = 1e-8\nprecision = 100\nshow_progress = 0\nbundle_eps_frac = 0.01\n",
+    },
+}

@@ -114,3 +114,81 @@ def test_reference_acceptance_test_passes_on_the_gpu():
     assert "PASS" in p.stdout
     p = subprocess.run([os.path.join(BUILT, "integrator_perf_test")], capture_output=True, text=True, env=env, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE configs 2 and 4 at application level: the reference's FITS-writing programs, built unchanged against the
+# shim (+ the bundled minimal FITS writer, cfitsio being absent), run on the B200 and compared with the FITS files
+# the reference's own CPU build wrote for the same par files (tests/golden/app_*.fits, scripts/make_golden.py).
+# ---------------------------------------------------------------------------------------------------------
+def run_app(exe, partext, tmp):
+    out = os.path.join(tmp, "out.fits")
+    par = os.path.join(tmp, "run.par")
+    with open(par, "w") as f:
+        f.write(f"outfile = {out}\n" + partext)
+    env = dict(os.environ, KERRTRACE_QUIET="1")
+    p = subprocess.run([os.path.join(BUILT, exe), f"--parfile={par}"], cwd=tmp, capture_output=True, text=True, env=env, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    from fits_reader import by_extname, read_fits
+    hdus = read_fits(out)
+    return hdus[0][0], by_extname(hdus)
+
+
+def close_fraction(a, b, rtol, mask):
+    a, b = a[mask], b[mask]
+    ok = np.abs(a - b) <= rtol * np.maximum(np.abs(b), 1e-12)
+    return ok.mean() if ok.size else 1.0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(BUILT, "imageplane_disc_image")), reason="shim/_built not present")
+def test_reference_imageplane_disc_image_app_on_the_gpu():
+    from fits_reader import by_extname, read_fits
+    from golden_cases import APP_PARS
+    want_h = read_fits(os.path.join(GOLDEN, "app_image_rk4.fits"))
+    want = by_extname(want_h)
+    with tempfile.TemporaryDirectory() as tmp:
+        prim, got = run_app("imageplane_disc_image", APP_PARS["imageplane_disc_image"]["app_image_rk4"], tmp)
+    assert list(got) == ["FLUX", "RADIUS", "PHI", "ENSHIFT", "TIME", "EMIS"] == list(want)      # the python notebooks' contract
+    for k in ("DIST", "INCL", "SPIN", "ISCO", "RDISC", "NRAYS"):
+        assert prim[k] == want_h[0][0][k], k
+    assert abs(prim["DISCRAYS"] - want_h[0][0]["DISCRAYS"]) <= 0.01 * want_h[0][0]["DISCRAYS"]
+    keep = np.ones((48, 48), dtype=bool)
+    keep[23, :] = False                         # pixels fed by the degenerate y = 0 rays (flip_image: 48 - 24 - 1)
+    hit_g, hit_w = np.isfinite(got["RADIUS"]), np.isfinite(want["RADIUS"])        # 0/0 = NaN where no ray hit (array.h:176-186)
+    assert (hit_g != hit_w)[keep].sum() <= 0.005 * keep.sum()
+    both = hit_g & hit_w & keep
+    assert both.sum() > 1000
+    for name in want:
+        tol = 1e-9
+        frac = close_fraction(got[name], want[name], tol, both)
+        assert frac >= 0.99, (name, frac)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(BUILT, "caustic_discplane")), reason="shim/_built not present")
+@pytest.mark.parametrize("case,n", [("app_caustic_rk4", 41), ("app_caustic_rk45", 25)])
+def test_reference_caustic_discplane_app_on_the_gpu(case, n):
+    from fits_reader import by_extname, read_fits
+    from golden_cases import APP_PARS
+    want_h = read_fits(os.path.join(GOLDEN, case + ".fits"))
+    want = by_extname(want_h)
+    with tempfile.TemporaryDirectory() as tmp:
+        prim, got = run_app("caustic_discplane", APP_PARS["caustic_discplane"][case], tmp)
+    names = ["DET_J", "SIGN_J", "ORDER", "HIT", "RADIUS", "PHI", "X_DISC", "Y_DISC", "REDSHIFT"]       # python/caustic_discplane.py:38-54
+    assert list(got) == names == list(want)
+    assert prim["NRAYS"] == want_h[0][0]["NRAYS"] == n * n
+    keep = np.ones((n, n), dtype=bool)
+    keep[n // 2, :] = False                      # the degenerate y = 0 bundle centres
+    rk45 = "rk45" in case
+    assert (got["HIT"] != want["HIT"])[keep].mean() <= (0.02 if rk45 else 0.01)
+    both = (got["HIT"] > 0) & (want["HIT"] > 0) & keep
+    tol = 1e-6 if rk45 else 1e-9
+    for name in ("RADIUS", "PHI", "X_DISC", "Y_DISC", "REDSHIFT"):
+        frac = close_fraction(got[name], want[name], tol, both)
+        assert frac >= (0.95 if rk45 else 0.98), (name, frac)
+    assert (got["ORDER"] == want["ORDER"])[both].mean() >= 0.98
+    # Jacobian determinant from the east/west/north/south satellites: finite differences over eps = 1 % of a pixel
+    # amplify the per-ray differences by ~1/eps
+    assert close_fraction(got["DET_J"], want["DET_J"], 1e-3 if rk45 else 1e-6, both) >= (0.90 if rk45 else 0.96)
+    assert (got["SIGN_J"] == want["SIGN_J"])[both].mean() >= 0.97
