@@ -214,6 +214,9 @@ int kt_sm_count(kt_ctx*);
 int64_t kt_kernel_launches(kt_ctx*);    /* number of kernels this ctx has launched so far */
 /* DFMA micro-benchmark: measured FP64 FMA peak in TFLOP/s (2 flop per FMA) -- the roofline denominator. */
 int kt_fp64_peak(kt_ctx*, double* tflops);
+/* bit-exactness self-test of the engine's IEEE division / square root (see csrc/kt_device.cuh: xdiv, xsqrt):
+ * counts[5] = {wrong quotients, wrong roots, quotients sent to the slow path, roots sent to the slow path, samples} */
+int kt_selftest_divsqrt(kt_ctx*, int mode, int samples_per_thread, int64_t* counts);
 /* dependent-issue latency of one DFMA in SM cycles (one warp, serial chain): explains the latency-bound regime */
 int kt_fp64_latency(kt_ctx*, double* cycles_per_op);
 /* tuning: resident 128-thread CTAs per SM the trace kernel is built for (3, 4 or 5; 0 = default).  Also

@@ -963,6 +963,23 @@ extern "C" int kt_fp64_latency(kt_ctx* c, double* cycles_per_op)
     return KT_OK;
 }
 
+// Bit-exactness self-test of the deferred-guard division / square root used by the exact arithmetic mode.
+// mode 0: operands uniform over all bit patterns; 1: moderate exponents; 2: with special values.
+// counts[5] = {wrong quotients, wrong roots, quotients sent to the slow path, roots sent to the slow path, samples}
+extern "C" int kt_selftest_divsqrt(kt_ctx* c, int mode, int samples_per_thread, int64_t* counts)
+{
+    if (int rc = ctx_bind(c)) return rc;
+    if (!counts) return fail(KT_ERR_INVALID, "null output");
+    KT_CUDA(cudaMemsetAsync(c->d_scratch, 0, 5 * sizeof(unsigned long long), c->stream));
+    KT_CUDA(kt_kernel_table_exact()->dfma_peak(cfg_of(c), c->d_scratch, -2, mode, samples_per_thread));
+    c->launches++;
+    unsigned long long h[5];
+    KT_CUDA(cudaMemcpyAsync(h, c->d_scratch, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 5; i++) counts[i] = (int64_t)h[i];
+    return KT_OK;
+}
+
 // sizeof() of every POD struct of the ABI, so bindings can check their mirrors (tests/test_abi.py)
 extern "C" int kt_abi_sizeof(const char* name)
 {

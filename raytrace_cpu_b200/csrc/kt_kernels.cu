@@ -534,6 +534,49 @@ __global__ void k_dfma_latency(double* out, int iters)
     if (threadIdx.x == 0) { out[0] = (double)(t1 - t0); out[1] = (double)iters * 32.0; out[2] = a; }
 }
 
+// Self-test of xdiv / xsqrt (exact mode): random operands over the whole exponent range plus special values.
+// out[0] = divisions where the guard accepted but the result differs from a / b   (must be 0)
+// out[1] = square roots where the guard accepted but the result differs from sqrt(a) (must be 0)
+// out[2] = divisions rejected by the guard, out[3] = square roots rejected, out[4] = samples
+__global__ void k_selftest_divsqrt(unsigned long long* out, unsigned long long seed, int per_thread, int mode)
+{
+#if !KT_FAST
+    unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+    auto next = [&]() {
+        x += 0x9E3779B97F4A7C15ull;
+        unsigned long long z = x;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    unsigned long long bad_d = 0, bad_s = 0, rej_d = 0, rej_s = 0;
+    for (int i = 0; i < per_thread; i++) {
+        unsigned long long ua = next(), ub = next();
+        if (mode == 1) {            // moderate exponents (what the integrator sees): 2^-40 .. 2^40
+            ua = (ua & 0x800fffffffffffffull) | ((unsigned long long)(1023 - 40 + (next() % 81)) << 52);
+            ub = (ub & 0x800fffffffffffffull) | ((unsigned long long)(1023 - 40 + (next() % 81)) << 52);
+        } else if (mode == 2 && (i & 7) == 0) {   // sprinkle special values
+            const unsigned long long sp[8] = {0ull, 0x8000000000000000ull, 0x7ff0000000000000ull, 0xfff0000000000000ull,
+                                              0x7ff8000000000000ull, 1ull, 0x000fffffffffffffull, 0x7fefffffffffffffull};
+            if (i & 8) ua = sp[next() & 7]; else ub = sp[next() & 7];
+        }
+        const double a = __longlong_as_double((long long)ua), b = __longlong_as_double((long long)ub);
+        bool ok = true;
+        const double q = xdiv(a, b, ok);
+        const double qr = a / b;
+        if (!ok) rej_d++;
+        else if (__double_as_longlong(q) != __double_as_longlong(qr) && !(q != q && qr != qr)) bad_d++;
+        bool oks = true;
+        const double s = xsqrt(a, oks);
+        const double sr = sqrt(a);
+        if (!oks) rej_s++;
+        else if (__double_as_longlong(s) != __double_as_longlong(sr) && !(s != s && sr != sr)) bad_s++;
+    }
+    atomicAdd(&out[0], bad_d); atomicAdd(&out[1], bad_s); atomicAdd(&out[2], rej_d); atomicAdd(&out[3], rej_s);
+    atomicAdd(&out[4], (unsigned long long)per_thread);
+#endif
+}
+
 // =========================================================================================================
 // Launchers
 // =========================================================================================================
@@ -675,6 +718,10 @@ static cudaError_t l_bin_image(const LaunchCfg& cfg, const kt_ray* rays, long lo
 }
 static cudaError_t l_dfma_peak(const LaunchCfg& cfg, double* out, int blocks, int threads, int iters)
 {
+    if (blocks < -1) {  // self-test of xdiv / xsqrt: threads = sampling mode, iters = samples per thread
+        k_selftest_divsqrt<<<cfg.sm_count * 8, 256, 0, cfg.stream>>>(reinterpret_cast<unsigned long long*>(out), 0x1234567ull + threads, iters, threads);
+        return cudaGetLastError();
+    }
     if (blocks < 0) {   // latency mode: one warp, dependent chain
         k_dfma_latency<<<1, 32, 0, cfg.stream>>>(out, iters);
         return cudaGetLastError();

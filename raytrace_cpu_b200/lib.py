@@ -21,7 +21,7 @@ class KerrtraceError(RuntimeError):
 # every symbol include/kerrtrace.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = [
     "kt_device_count", "kt_create", "kt_destroy", "kt_last_error", "kt_version", "kt_set_stream", "kt_synchronize",
-    "kt_sm_count", "kt_kernel_launches", "kt_fp64_peak", "kt_fp64_latency", "kt_set_min_blocks", "kt_host_alloc", "kt_host_free",
+    "kt_sm_count", "kt_kernel_launches", "kt_fp64_peak", "kt_fp64_latency", "kt_selftest_divsqrt", "kt_set_min_blocks", "kt_host_alloc", "kt_host_free",
     "kt_abi_sizeof", "kt_set_timeout", "kt_aborted", "kt_tracer_init", "kt_kerr_horizon", "kt_kerr_isco", "kt_pointsource_count", "kt_imageplane_count",
     "kt_rayset_create", "kt_rayset_destroy", "kt_rayset_count", "kt_rayset_device_ptr", "kt_rayset_upload",
     "kt_rayset_download", "kt_rayset_init_pointsource", "kt_rayset_init_imageplane", "kt_rayset_redshift_start",
@@ -67,6 +67,7 @@ def load():
     proto("kt_kernel_launches", i64, vp)
     proto("kt_fp64_peak", i32, vp, A.c_double_p)
     proto("kt_fp64_latency", i32, vp, A.c_double_p)
+    proto("kt_selftest_divsqrt", i32, vp, i32, i32, A.c_int64_p)
     proto("kt_set_min_blocks", i32, vp, i32)
     proto("kt_host_alloc", vp, C.c_size_t)
     proto("kt_host_free", None, vp)
