@@ -107,8 +107,16 @@ typedef struct kt_run {
     int32_t steplim;    /* <= 0: STEPLIM for RK4, RK45_STEPLIM for RK45 (raytracer.cpp:80) */
     double r_max;
     int32_t math_mode;  /* KT_MATH_EXACT (default 0) or KT_MATH_FAST */
-    int32_t _pad;
+    int32_t flags;      /* 0 (reference behaviour) or KT_RUN_RETIRE_STUCK */
 } kt_run;
+
+/* Opt-in, NOT reference behaviour: under RK45 a ray falling into the hole never crosses the horizon --
+ * the per-step cap |r - r_h| / |pr| / precision has no floor (raytracer.cpp:1421-1434), so it creeps for RK45_STEPLIM =
+ * 100 000 steps and ends as a step-limit failure (steps < 0), which every consumer discards.  At h = 10 these are 1-4 % of
+ * the rays and 77-93 % of all steps.  With this flag an ingoing ray closer to the horizon than 1e-4 of the gap to the
+ * innermost photon orbit (below which no radial turning point exists) is retired at once with STEPLIM set and its step
+ * count negated: the same rays fail, after ~1 500 steps instead of 100 000; histograms and images are unchanged. */
+#define KT_RUN_RETIRE_STUCK 1
 
 /* PointSource<T> constructor arguments: pointsource.h:24, pointsource.cpp:11-64. */
 typedef struct kt_pointsource {

@@ -35,6 +35,7 @@ MIN_STEP = 1e-3
 EULER, RK4, RK45 = 0, 1, 2
 STOP_THETALIM, STOP_FLATDISC, STOP_ISCODISC, STOP_FLATPLANE = 0, 1, 2, 3
 MATH_EXACT, MATH_FAST = 0, 1
+RUN_RETIRE_STUCK = 1
 HIT_Z, HIT_THETA, HIT_DEST = 0, 1, 2
 REDSHIFT_V, REDSHIFT_DEST = 0, 1
 CNT_SLOTS, CNT_TRACED, CNT_STEPS, CNT_DEST, CNT_HORIZON, CNT_RLIM, CNT_STEPLIM, CNT_DISC = range(8)
@@ -84,7 +85,7 @@ class Tracer(C.Structure):
 class Run(C.Structure):
     _fields_ = [
         ("integrator", C.c_int32), ("steplim", C.c_int32), ("r_max", C.c_double),
-        ("math_mode", C.c_int32), ("_pad", C.c_int32),
+        ("math_mode", C.c_int32), ("flags", C.c_int32),
     ]
 
 

@@ -181,9 +181,9 @@ def thetalim_stop(theta_max):
     return s
 
 
-def make_run(method, r_max, steplim=-1, math_mode=A.MATH_EXACT):
+def make_run(method, r_max, steplim=-1, math_mode=A.MATH_EXACT, flags=0):
     r = A.Run()
-    r.integrator, r.r_max, r.steplim, r.math_mode = int(method), r_max, steplim, math_mode
+    r.integrator, r.r_max, r.steplim, r.math_mode, r.flags = int(method), r_max, steplim, math_mode, flags
     return r
 
 
@@ -460,7 +460,7 @@ def bin_radii(bins):
 
 
 def emissivity(src, spin, bins, method=Integrator.RK4, stop=None, r_max=1000.0, tol=A.TOL, steplim=-1, rk45_tol=None,
-               shard=None, ctx=None, math_mode=A.MATH_EXACT, tracer=None):
+               shard=None, ctx=None, math_mode=A.MATH_EXACT, tracer=None, flags=0):
     """Whole emissivity app in one kernel: PointSource -> trace -> redshift -> radial histogram (raw sums)."""
     ctx = ctx or get_context()
     tr = tracer or make_tracer(spin, tol)
@@ -469,7 +469,7 @@ def emissivity(src, spin, bins, method=Integrator.RK4, stop=None, r_max=1000.0, 
     stop = stop if stop is not None else thetalim_stop(M_PI_2)
     if isinstance(stop, RayDestination):
         stop = stop._stop()
-    run = make_run(method, r_max, steplim, math_mode)
+    run = make_run(method, r_max, steplim, math_mode, flags)
     out = A.EmisResult(bins.Nr)
     check(ctx.L.kt_pointsource_emissivity(ctx.h, C.byref(src), C.byref(tr), C.byref(stop), C.byref(run), C.byref(bins),
                                           C.byref(shard) if shard is not None else None, C.byref(out.c)))

@@ -344,6 +344,12 @@ static int make_params(TraceParams& P, const kt_tracer* tr, const kt_stop* stop,
     }
     if (stop && (stop->kind < KT_STOP_THETALIM || stop->kind > KT_STOP_FLATPLANE)) return fail(KT_ERR_INVALID, "unknown stop kind %d", stop->kind);
     const double a = tr->spin;
+    if (run && (run->flags & KT_RUN_RETIRE_STUCK) && run->integrator == KT_RK45) {
+        // innermost (prograde) circular photon orbit of |a|: no radial turning point exists below it
+        const double r_ph = 2 * (1 + std::cos(2.0 / 3.0 * std::acos(-std::fabs(a) > -1 ? -std::fabs(a) : -1.0)));
+        const double gap = r_ph - tr->horizon;
+        P.stuck_eps = gap > 0 ? 1e-4 * gap : 0.0;
+    }
     P.a = a;
     P.two_a = 2 * a;
     P.two_a_a = 2 * a * a;

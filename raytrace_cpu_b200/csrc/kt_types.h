@@ -15,6 +15,7 @@ struct TraceParams {
     int integrator;
     // loop invariants pre-multiplied exactly as the reference's expressions associate: 2*a, (2*a)*a, a*a
     double a, two_a, two_a_a, aa;
+    double stuck_eps;   // KT_RUN_RETIRE_STUCK: retire ingoing RK45 rays with r - horizon < stuck_eps (0 = off)
     // work queue
     unsigned long long* queue;
     long long n_work;   // number of work ordinals this launch hands out
