@@ -31,7 +31,7 @@ extern "C" {
 #define KT_ERR_INVALID (-1)     /* bad argument */
 #define KT_ERR_CUDA (-2)        /* CUDA runtime error (message has the cudaError string) */
 #define KT_ERR_NOMEM (-3)       /* host or device allocation failed */
-#define KT_ERR_UNSUPPORTED (-4) /* valid in the reference but not offloaded (Euler, ray-path dumping) */
+#define KT_ERR_UNSUPPORTED (-4) /* valid in the reference but not offloaded (user-defined RayDestination subclasses) */
 #define KT_ERR_TIMEOUT (-5)     /* the optional watchdog fired: a trace kernel abandoned its launch */
 
 /* ---- ray status bit flags: raytracer.h:58-63 ---- */
@@ -103,7 +103,7 @@ typedef struct kt_tracer {
 
 /* Arguments of one run_raytrace() call. */
 typedef struct kt_run {
-    int32_t integrator; /* KT_RK4 or KT_RK45 (KT_EULER -> KT_ERR_UNSUPPORTED) */
+    int32_t integrator; /* KT_EULER (theta_max stop only, as raytracer.cpp:983 asserts), KT_RK4 or KT_RK45 */
     int32_t steplim;    /* <= 0: STEPLIM for RK4, RK45_STEPLIM for RK45 (raytracer.cpp:80) */
     double r_max;
     int32_t math_mode;  /* KT_MATH_EXACT (default 0) or KT_MATH_FAST */
@@ -201,11 +201,45 @@ typedef struct kt_image_out {
     int64_t counters[KT_NCOUNTERS];
 } kt_image_out;
 
+/* Ray-path dumping: the `outfile, write_step, write_rmax, write_rmin, write_cartesian` arguments of run_raytrace
+ * (raytracer.cpp:63-68) and the write blocks of the five propagators (raytracer.cpp:293-312, 923-942, 1209-1228,
+ * 1552-1571, 1850-1869).  After every write_step-th step that neither crossed the horizon nor reached the destination
+ * a ray inside the radial window writes one point: (t, x, y, z) through cartesian() (kerr.h:40-56) when write_cartesian,
+ * else (t, r, theta, phi).  A ray that leaves the window after its first point stops there. */
+typedef struct kt_path_opts {
+    int32_t write_step;
+    int32_t write_cartesian;
+    double write_rmax, write_rmin; /* < 0: unbounded */
+} kt_path_opts;
+
 /* Compact per-ray result for source-generated rays (caustic maps, parity tests): 56 bytes instead of 144. */
 typedef struct kt_ray_min {
     double r, theta, phi, t, redshift;
     int32_t steps, status, rdot_flips, equatorial_crossings;
 } kt_ray_min;
+
+/* Caustic / critical-curve maps of the image plane: caustic_discplane.cpp:146-202 (per-pixel maps and the two
+ * helper predicates), :209-334 (bundle Jacobian from the east/west/north/south satellite rays, kt_imageplane::bundles = 1),
+ * :337-448 (grid-neighbour Jacobian, bundles = 0) and :451-493 (suppression of alternating-sign pixels).
+ * Maps are [ix * img_Ny + iy] like Array2D. */
+#define KT_CAUSTIC_SENTINEL 1e30    /* det_J where the image order changes inside the stencil (caustic_discplane.cpp:152) */
+typedef struct kt_caustic_cfg {
+    int32_t img_Nx, img_Ny;    /* rays per axis: the app's Nx + 1, Ny + 1 (caustic_discplane.cpp:129-130) */
+    double r_isco, r_disc;     /* valid_hit: steps > 0, r_isco <= r < r_disc, redshift > 0 (caustic_discplane.cpp:177-182) */
+    double dx, dy;             /* grid spacing, the denominators of the grid-neighbour Jacobian (caustic_discplane.cpp:435-438) */
+    int32_t redshift_mode;     /* KT_REDSHIFT_DEST as the app (caustic_discplane.cpp:217) or KT_REDSHIFT_V with V */
+    int32_t suppress;          /* 1: run the alternating-sign suppression pass (the app always does) */
+    double V;
+} kt_caustic_cfg;
+typedef struct kt_caustic_out {
+    double *det_J, *sign_J;    /* NaN / 0 where undefined, KT_CAUSTIC_SENTINEL / 0 at order boundaries */
+    int32_t *order, *hit;      /* order = max(floor(|phi| / 2 pi), rdot_flips / 2), -1 where no hit */
+    double *radius, *phi, *x_disc, *y_disc, *redshift;
+    int64_t disc_count;        /* pixels whose centre ray hit the disc */
+    int64_t cnt_horizon, cnt_rlim, cnt_steplim, cnt_outofrange, cnt_other; /* the app's diagnostic line (caustic_discplane.cpp:256-274) */
+    int64_t suppressed;
+    int64_t counters[KT_NCOUNTERS];
+} kt_caustic_out;
 
 typedef struct kt_ctx kt_ctx;
 typedef struct kt_rayset kt_rayset;
@@ -270,6 +304,19 @@ int kt_rayset_bin_image(kt_rayset*, const kt_image_bins*, kt_image_out* host_out
 
 /* ---- host-buffer entry points (what the shim's Raytracer<double> methods call; copies included) ---- */
 int kt_trace(kt_ctx*, const kt_tracer*, const kt_stop*, const kt_run*, kt_ray* rays, int64_t n);
+/* run_raytrace(..., outfile != 0, write_step, write_rmax, write_rmin, write_cartesian), the serial ordered-output path
+ * (raytracer.cpp:86-100, 995-1008), in two calls so that the caller owns every buffer:
+ *   kt_trace_paths_count: offsets[n + 1] = exclusive prefix sums of the number of points each ray writes (offsets[n] =
+ *                         total); `rays` is not modified.
+ *   kt_trace_paths      : the trace itself -- `rays` updated in place exactly as kt_trace does, and ray i's points
+ *                         written to points[4 * offsets[i] .. 4 * offsets[i + 1]) in step order.
+ * The caller then emits the text (ray order, points, two blank lines after every ray that was propagated: rays with
+ * steps < 0 or steps >= steplim are skipped entirely, raytracer.cpp:91-92,99) -- the shim's Raytracer does exactly that
+ * through the reference's own TextOutput. */
+int kt_trace_paths_count(kt_ctx*, const kt_tracer*, const kt_stop*, const kt_run*, const kt_ray* rays, int64_t n,
+                         const kt_path_opts*, int64_t* offsets);
+int kt_trace_paths(kt_ctx*, const kt_tracer*, const kt_stop*, const kt_run*, kt_ray* rays, int64_t n, const kt_path_opts*,
+                   const int64_t* offsets, double* points);
 int kt_redshift_start(kt_ctx*, const kt_tracer*, kt_ray* rays, int64_t n, double V, int reverse, int projradius);
 int kt_redshift(kt_ctx*, const kt_tracer*, kt_ray* rays, int64_t n, double V, int reverse, int projradius, int motion);
 int kt_redshift_dest(kt_ctx*, const kt_tracer*, const kt_stop*, kt_ray* rays, int64_t n, int reverse);
@@ -297,6 +344,11 @@ int kt_imageplane_image_dev(kt_ctx*, const kt_imageplane*, const kt_tracer*, con
 /* redshift_mode: KT_REDSHIFT_V with V (apps pass -1) or KT_REDSHIFT_DEST; reverse is always true for planes. */
 int kt_imageplane_rays(kt_ctx*, const kt_imageplane*, const kt_tracer*, const kt_stop*, const kt_run*,
                        int redshift_mode, double V, int range_phi, kt_ray_min* host_out, int64_t n);
+
+/* kt_caustic_discplane == caustic_discplane.cpp:204-493 in one call: image plane (or bundles) -> trace -> redshift ->
+ * per-pixel maps -> Jacobian determinant -> suppression pass, all on the device; only the nine maps come back. */
+int kt_caustic_discplane(kt_ctx*, const kt_imageplane*, const kt_tracer*, const kt_stop*, const kt_run*, const kt_caustic_cfg*,
+                         kt_caustic_out* host_out);
 
 #ifdef __cplusplus
 }

@@ -470,8 +470,127 @@ static inline int theta_inside(double thetalim, double th)
     return (thetalim > 0 && th < thetalim) || (thetalim < 0 && th > fabs(thetalim)) || thetalim == 0;
 }
 
+/* Ray-path dumping, the `outfile` blocks of the propagators (raytracer.cpp:293-312, 923-942, 1209-1228, 1552-1571,
+ * 1850-1869): every write_step-th step inside the radial window writes one point; a ray that leaves the window after
+ * its first point stops.  Points are (t, x, y, z) through cartesian() (kerr.h:40-56) or (t, r, theta, phi).
+ * sink == NULL: no dumping.  pts == NULL: count only. */
+typedef struct path_sink {
+    const kt_path_opts* o;
+    double* pts;     /* 4 doubles per point, or NULL */
+    int64_t n;       /* points written so far */
+    int started;
+} path_sink;
+
+static inline int path_point(path_sink* k, int steps, double t, double r, double th, double ph, double a)
+{
+    if (!k || (steps % k->o->write_step) != 0) return 0;
+    if ((k->o->write_rmax < 0 || r < k->o->write_rmax) && (k->o->write_rmin < 0 || r > k->o->write_rmin)) {
+        k->started = 1;
+        if (k->pts) {
+            double* p = k->pts + 4 * k->n;
+            p[0] = t;
+            if (k->o->write_cartesian) {
+                p[1] = sqrt(r * r + a * a) * sin(th) * cos(ph);
+                p[2] = sqrt(r * r + a * a) * sin(th) * sin(ph);
+                p[3] = r * cos(th);
+            } else {
+                p[1] = r; p[2] = th; p[3] = ph;
+            }
+        }
+        k->n++;
+        return 0;
+    }
+    return k->started;
+}
+
+/* Euler: Raytracer::propagate, raytracer.cpp:129-340 (theta_max overload only: raytracer.cpp:983 asserts that Euler is
+ * never combined with a RayDestination) */
+static int trace_euler(kt_ray* q, const kt_tracer* tr, const kt_stop* stop, double rlim, int steplim, path_sink* sink)
+{
+    const double thetalim = stop->theta_lim;
+    const double a = tr->spin, horizon = tr->horizon;
+    const double k = q->k, h = q->h, Q = q->Q;
+    double t = q->t, r = q->r, th = q->theta, ph = q->phi;
+    double pt = q->pt, pr = q->pr, pth = q->ptheta, pph = q->pphi;
+    int sr = q->rdot_sign, sth = q->thetadot_sign, flips = q->rdot_flips, cross = q->equatorial_crossings;
+    int status = q->status;
+    int r_seen_pos = 0, th_seen_pos = 1;
+    int steps = 0;
+
+    while (r < rlim && theta_inside(thetalim, th) && steps < steplim) {
+        ++steps;
+        const double sn = sin(th), cs = cos(th), sn2 = sn * sn;
+        const double rho2 = r * r + (a * cs) * (a * cs);
+        const double del = r * r - 2 * r + a * a;
+        const double rho2del = rho2 * del;
+
+        pt = (rho2 * (r * r + a * a) + 2 * a * a * r * sn2) * k - 2 * a * r * h;
+        pt /= rho2del;
+        pph = 2 * a * r * sn2 * k + (rho2 - 2 * r) * h;
+        pph /= sn2 * rho2del;
+
+        double thsq = Q + (k * a * cs + h * cs / sn) * (k * a * cs - h * cs / sn);
+        thsq = thsq / (rho2 * rho2);
+        if (thsq < 0 && th_seen_pos) {
+            sth *= -1;
+            th_seen_pos = 0;
+            continue;
+        }
+        if (thsq >= 0) th_seen_pos = 1;
+        pth = sqrt(fabs(thsq)) * sth;
+
+        double rsq = k * pt - h * pph - rho2 * pth * pth;
+        rsq = rsq * del / rho2;
+        if (rsq <= 0 && r_seen_pos) {
+            sr *= -1;
+            r_seen_pos = 0;
+            flips++;
+        } else if (rsq > 0) {
+            r_seen_pos = 1;
+        }
+        pr = sqrt(fabs(rsq)) * sr;
+
+        double step = fabs((r - horizon) / pr) / tr->precision;
+        if (step > fabs(th / pth) / tr->precision) step = fabs(th / pth) / tr->theta_precision;
+        if (tr->max_tstep > 0 && r < tr->maxtstep_rlim && step > fabs(tr->max_tstep / pt)) step = fabs(tr->max_tstep / pt);
+        if (tr->max_phistep > 0 && step > fabs(tr->max_phistep / pph)) step = fabs(tr->max_phistep / pph);
+        if (step < KT_MIN_STEP) step = KT_MIN_STEP;
+        if (rlim > 0 && r + pr * step > rlim) step = fabs((rlim - r) / pr);
+        if (thetalim > 0 && th + pth * step > thetalim) step = fabs((thetalim - th) / pth);
+
+        if (pt <= 0) status |= KT_STATUS_ERGO;
+        if ((1 - 2 * r / rho2) * pt + (2 * a * r * sn2 / rho2) * pph < 0) status |= KT_STATUS_NEG_ENERGY;
+
+        t += pt * step;
+        r += pr * step;
+        {
+            const double tep = th;
+            th += pth * step;
+            if ((tep < ORC_PI_2 && th >= ORC_PI_2) || (tep > ORC_PI_2 && th <= ORC_PI_2)) ++cross;
+        }
+        ph += pph * step;
+        if (th < 0) { th = -th; sth = -sth; ph += ORC_PI; }
+        if (th > ORC_PI) { th = 2.0 * ORC_PI - th; sth = -sth; ph += ORC_PI; }
+
+        if (r <= horizon) { status |= KT_STATUS_HORIZON; break; }
+        if (path_point(sink, steps, t, r, th, ph, a)) break;
+    }
+
+    if (steps >= steplim) status |= KT_STATUS_STEPLIM;
+    else if (r >= rlim) status |= KT_STATUS_RLIM;
+    else if ((thetalim > 0 && th >= thetalim) || (thetalim < 0 && th <= fabs(thetalim))) status |= KT_STATUS_DEST;
+
+    q->t = t; q->r = r; q->theta = th; q->phi = ph;
+    q->pt = pt; q->pr = pr; q->ptheta = pth; q->pphi = pph;
+    q->rdot_sign = sr; q->thetadot_sign = sth; q->rdot_flips = flips; q->equatorial_crossings = cross;
+    q->status = status;
+    if (steps > 0) q->steps += steps;
+    if (status & KT_STATUS_STEPLIM) q->steps = -q->steps;
+    return steps;
+}
+
 /* RK4: raytracer.cpp:755-970 (theta_max overload) and :1036-1254 (destination overload) */
-static int trace_rk4(kt_ray* q, const kt_tracer* tr, const kt_stop* stop, double rlim, int steplim)
+static int trace_rk4(kt_ray* q, const kt_tracer* tr, const kt_stop* stop, double rlim, int steplim, path_sink* sink)
 {
     const int use_dest = stop->kind != KT_STOP_THETALIM;
     const double thetalim = stop->theta_lim;
@@ -545,6 +664,7 @@ static int trace_rk4(kt_ray* q, const kt_tracer* tr, const kt_stop* stop, double
 
         if (r <= horizon) { status |= KT_STATUS_HORIZON; break; }
         if (use_dest && dest_reached(stop, r, th, ph, th_prev)) { status |= KT_STATUS_DEST; break; }
+        if (path_point(sink, steps, t, r, th, ph, a)) break;
     }
 
     if (steps >= steplim) status |= KT_STATUS_STEPLIM;
@@ -594,7 +714,7 @@ static inline double dmax(double x, double y) { return (x < y) ? y : x; } /* std
 static inline double dmin(double x, double y) { return (y < x) ? y : x; } /* std::min */
 
 /* RK45: raytracer.cpp:1260-1598 (theta_max overload) and :1600-1894 (destination overload) */
-static int trace_rk45(kt_ray* q, const kt_tracer* tr, const kt_stop* stop, double rlim, int steplim)
+static int trace_rk45(kt_ray* q, const kt_tracer* tr, const kt_stop* stop, double rlim, int steplim, path_sink* sink)
 {
     const int use_dest = stop->kind != KT_STOP_THETALIM;
     const double thetalim = stop->theta_lim;
@@ -742,6 +862,7 @@ static int trace_rk45(kt_ray* q, const kt_tracer* tr, const kt_stop* stop, doubl
 
         if (r <= horizon) { status |= KT_STATUS_HORIZON; break; }
         if (use_dest && dest_reached(stop, r, th, ph, th_prev)) { status |= KT_STATUS_DEST; break; }
+        if (path_point(sink, steps, t, r, th, ph, a)) break;
     }
 
     if (steps >= steplim || poisoned) status |= KT_STATUS_STEPLIM;
@@ -772,11 +893,35 @@ int64_t orc_trace(kt_ray* rays, int64_t n, const kt_tracer* tr, const kt_stop* s
     for (int64_t i = 0; i < n; i++) {
         if (rays[i].steps < 0) continue;
         if (rays[i].steps >= steplim) continue;
-        if (rk45) trace_rk45(&rays[i], tr, stop, run->r_max, steplim);
-        else trace_rk4(&rays[i], tr, stop, run->r_max, steplim);
+        if (rk45) trace_rk45(&rays[i], tr, stop, run->r_max, steplim, NULL);
+        else if (run->integrator == KT_EULER) trace_euler(&rays[i], tr, stop, run->r_max, steplim, NULL);
+        else trace_rk4(&rays[i], tr, stop, run->r_max, steplim, NULL);
         traced++;
     }
     return traced;
+}
+
+/* run_raytrace, serial path with an outfile: raytracer.cpp:86-100 / :995-1008.  Rays are propagated in index order;
+ * offsets[i]..offsets[i+1] are the points ray i wrote (a skipped ray writes none -- and no blank lines either).
+ * points == NULL: count only (the rays are still propagated in place, so pass a scratch copy). */
+int64_t orc_trace_paths(kt_ray* rays, int64_t n, const kt_tracer* tr, const kt_stop* stop, const kt_run* run,
+                        const kt_path_opts* opts, int64_t* offsets, double* points)
+{
+    const int rk45 = run->integrator == KT_RK45;
+    const int steplim = (run->steplim > 0) ? run->steplim : (rk45 ? KT_RK45_STEPLIM : KT_STEPLIM);
+    int64_t total = 0;
+    for (int64_t i = 0; i < n; i++) {
+        offsets[i] = total;
+        if (rays[i].steps < 0) continue;
+        if (rays[i].steps >= steplim) continue;
+        path_sink k = {opts, points ? points + 4 * total : NULL, 0, 0};
+        if (rk45) trace_rk45(&rays[i], tr, stop, run->r_max, steplim, &k);
+        else if (run->integrator == KT_EULER) trace_euler(&rays[i], tr, stop, run->r_max, steplim, &k);
+        else trace_rk4(&rays[i], tr, stop, run->r_max, steplim, &k);
+        total += k.n;
+    }
+    offsets[n] = total;
+    return total;
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -873,4 +1018,137 @@ void orc_bin_image(const kt_ray* rays, int64_t n, const kt_image_bins* b, kt_ima
             }
         }
     }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* caustic / critical-curve maps: caustic_discplane.cpp:146-493                                       */
+/* ------------------------------------------------------------------------------------------------ */
+static inline int caustic_valid_hit(const kt_ray* q, const kt_caustic_cfg* c) /* caustic_discplane.cpp:177-182 */
+{
+    return q->steps > 0 && q->r >= c->r_isco && q->r < c->r_disc && q->redshift > 0;
+}
+
+static inline int caustic_order(const kt_ray* q) /* caustic_discplane.cpp:199-203 */
+{
+    const int phi_ord = (int)(fabs(q->phi) / (2 * ORC_PI));
+    const int r_ord = q->rdot_flips / 2;
+    return phi_ord > r_ord ? phi_ord : r_ord;
+}
+
+static inline void caustic_disc_xy(double phi_acc, double r, double* xd, double* yd) /* caustic_discplane.cpp:170-174 */
+{
+    const double phi_s = atan2(sin(phi_acc), cos(phi_acc));
+    *xd = r * cos(phi_s);
+    *yd = r * sin(phi_s);
+}
+
+void orc_caustic_maps(const kt_ray* rays, int64_t n, int32_t plane_Ny, int bundles, double eps_x, double eps_y,
+                      const kt_caustic_cfg* c, kt_caustic_out* o)
+{
+    const int Nx = c->img_Nx, Ny = c->img_Ny;
+    const int per = bundles ? 5 : 1;
+    static const kt_ray unused = {.steps = -1};
+#define RAY(ix, iy, sat) ((((int64_t)(ix) * plane_Ny + (iy)) * per + (sat)) < n ? &rays[((int64_t)(ix) * plane_Ny + (iy)) * per + (sat)] : &unused)
+#define PIX(ix, iy) ((int64_t)(ix) * Ny + (iy))
+    o->disc_count = o->cnt_horizon = o->cnt_rlim = o->cnt_steplim = o->cnt_outofrange = o->cnt_other = o->suppressed = 0;
+    /* centre rays: caustic_discplane.cpp:220-253 (bundles) / :351-381 (grid) */
+    for (int ix = 0; ix < Nx; ix++)
+        for (int iy = 0; iy < Ny; iy++) {
+            const kt_ray* q = RAY(ix, iy, 0);
+            const int64_t p = PIX(ix, iy);
+            if (caustic_valid_hit(q, c)) {
+                const double phi_s = atan2(sin(q->phi), cos(q->phi));
+                o->hit[p] = 1;
+                o->radius[p] = q->r;
+                o->phi[p] = phi_s;
+                o->x_disc[p] = q->r * cos(phi_s);
+                o->y_disc[p] = q->r * sin(phi_s);
+                o->order[p] = caustic_order(q);
+                o->redshift[p] = q->redshift;
+                ++o->disc_count;
+            } else {
+                o->hit[p] = 0;
+                o->radius[p] = o->phi[p] = o->x_disc[p] = o->y_disc[p] = o->redshift[p] = 0;
+                o->order[p] = -1;
+            }
+            /* diagnostic counts: caustic_discplane.cpp:256-274 */
+            if (q->steps > 0 && (q->r < c->r_isco || q->r >= c->r_disc || q->redshift <= 0)) ++o->cnt_outofrange;
+            else if (q->steps <= 0 || !(q->status & KT_STATUS_DEST)) {
+                if (q->status & KT_STATUS_HORIZON) ++o->cnt_horizon;
+                else if (q->status & KT_STATUS_RLIM) ++o->cnt_rlim;
+                else if (q->status & KT_STATUS_STEPLIM) ++o->cnt_steplim;
+                else ++o->cnt_other;
+            }
+        }
+    /* Jacobian */
+    for (int ix = 0; ix < Nx; ix++)
+        for (int iy = 0; iy < Ny; iy++) {
+            const int64_t p = PIX(ix, iy);
+            o->det_J[p] = NAN;
+            o->sign_J[p] = 0;
+            if (!o->hit[p]) continue;
+            double det;
+            if (bundles) { /* caustic_discplane.cpp:277-333 */
+                const kt_ray *re = RAY(ix, iy, 1), *rw = RAY(ix, iy, 2), *rn = RAY(ix, iy, 3), *rs = RAY(ix, iy, 4);
+                if (!caustic_valid_hit(re, c) || !caustic_valid_hit(rw, c) || !caustic_valid_hit(rn, c) || !caustic_valid_hit(rs, c))
+                    continue;
+                const kt_ray* rc = RAY(ix, iy, 0);
+                const int flips = rc->rdot_flips;
+                const double phi_c = rc->phi;
+                const int match = re->rdot_flips == flips && rw->rdot_flips == flips && rn->rdot_flips == flips &&
+                                  rs->rdot_flips == flips && fabs(re->phi - phi_c) < ORC_PI_2 && fabs(rw->phi - phi_c) < ORC_PI_2 &&
+                                  fabs(rn->phi - phi_c) < ORC_PI_2 && fabs(rs->phi - phi_c) < ORC_PI_2;
+                if (!match) { o->det_J[p] = KT_CAUSTIC_SENTINEL; continue; }
+                double xe, ye, xw, yw, xn, yn, xs, ys;
+                caustic_disc_xy(re->phi, re->r, &xe, &ye);
+                caustic_disc_xy(rw->phi, rw->r, &xw, &yw);
+                caustic_disc_xy(rn->phi, rn->r, &xn, &yn);
+                caustic_disc_xy(rs->phi, rs->r, &xs, &ys);
+                const double dxd_da = (xe - xw) / (2 * eps_x), dxd_db = (xn - xs) / (2 * eps_y);
+                const double dyd_da = (ye - yw) / (2 * eps_x), dyd_db = (yn - ys) / (2 * eps_y);
+                det = dxd_da * dyd_db - dxd_db * dyd_da;
+            } else { /* caustic_discplane.cpp:409-447 */
+                if (ix == 0 || ix == Nx - 1 || iy == 0 || iy == Ny - 1) continue;
+                const int64_t e = PIX(ix + 1, iy), w = PIX(ix - 1, iy), nn = PIX(ix, iy + 1), ss = PIX(ix, iy - 1);
+                if (!(o->hit[e] && o->hit[w] && o->hit[nn] && o->hit[ss])) continue;
+                const int ord = o->order[p];
+                if (!(o->order[e] == ord && o->order[w] == ord && o->order[nn] == ord && o->order[ss] == ord)) {
+                    o->det_J[p] = KT_CAUSTIC_SENTINEL;
+                    continue;
+                }
+                const double dxd_dx = (o->x_disc[e] - o->x_disc[w]) / (2 * c->dx), dxd_dy = (o->x_disc[nn] - o->x_disc[ss]) / (2 * c->dy);
+                const double dyd_dx = (o->y_disc[e] - o->y_disc[w]) / (2 * c->dx), dyd_dy = (o->y_disc[nn] - o->y_disc[ss]) / (2 * c->dy);
+                det = dxd_dx * dyd_dy - dxd_dy * dyd_dx;
+            }
+            o->det_J[p] = det;
+            o->sign_J[p] = (det > 0) ? 1.0 : (det < 0) ? -1.0 : 0.0;
+        }
+    /* suppression of alternating-sign pixels on a snapshot of sign_J: caustic_discplane.cpp:467-492 */
+    if (c->suppress) {
+        double* snap = (double*)malloc(sizeof(double) * (size_t)Nx * Ny);
+        memcpy(snap, o->sign_J, sizeof(double) * (size_t)Nx * Ny);
+        static const int dix[4] = {-1, 1, 0, 0}, diy[4] = {0, 0, -1, 1};
+        for (int ix = 0; ix < Nx; ix++)
+            for (int iy = 0; iy < Ny; iy++) {
+                const double s = snap[PIX(ix, iy)];
+                if (s == 0.0) continue;
+                int n_same = 0, n_opp = 0;
+                for (int d = 0; d < 4; d++) {
+                    const int jx = ix + dix[d], jy = iy + diy[d];
+                    if (jx < 0 || jx >= Nx || jy < 0 || jy >= Ny) continue;
+                    const double sn = snap[PIX(jx, jy)];
+                    if (sn == 0.0) continue;
+                    if (sn * s > 0) ++n_same;
+                    else ++n_opp;
+                }
+                if (n_opp > n_same && n_opp >= 2) {
+                    o->det_J[PIX(ix, iy)] = KT_CAUSTIC_SENTINEL;
+                    o->sign_J[PIX(ix, iy)] = 0.0;
+                    ++o->suppressed;
+                }
+            }
+        free(snap);
+    }
+#undef RAY
+#undef PIX
 }

@@ -33,12 +33,18 @@ void orc_imageplane_init(kt_ray* rays, int64_t n, const kt_tracer* tr, const kt_
 void orc_redshift_start(kt_ray* rays, int64_t n, const kt_tracer* tr, double V, int reverse, int projradius);
 /* returns the number of rays actually propagated; nthreads <= 0 -> OpenMP default */
 int64_t orc_trace(kt_ray* rays, int64_t n, const kt_tracer* tr, const kt_stop* stop, const kt_run* run, int nthreads);
+/* the serial `outfile` path of run_raytrace: offsets[n+1], points[4 * offsets[n]] (NULL = count only) */
+int64_t orc_trace_paths(kt_ray* rays, int64_t n, const kt_tracer* tr, const kt_stop* stop, const kt_run* run,
+                        const kt_path_opts* opts, int64_t* offsets, double* points);
 void orc_redshift(kt_ray* rays, int64_t n, const kt_tracer* tr, double V, int reverse, int projradius, int motion);
 void orc_redshift_dest(kt_ray* rays, int64_t n, const kt_tracer* tr, const kt_stop* stop, int reverse);
 void orc_range_phi(kt_ray* rays, int64_t n, double lo, double hi);
 void orc_calculate_momentum(kt_ray* rays, int64_t n, const kt_tracer* tr);
 void orc_bin_emissivity(const kt_ray* rays, int64_t n, const kt_emis_bins* b, kt_emis_out* out);
 void orc_bin_image(const kt_ray* rays, int64_t n, const kt_image_bins* b, kt_image_out* out);
+/* caustic_discplane.cpp:146-493 on an already traced + redshifted ray set (plane_Ny = ImagePlane::Ny) */
+void orc_caustic_maps(const kt_ray* rays, int64_t n, int32_t plane_Ny, int bundles, double eps_x, double eps_y,
+                      const kt_caustic_cfg* cfg, kt_caustic_out* out);
 void orc_momentum_from_consts(double* p4, double k, double h, double Q, int rdot_sign, int thetadot_sign, double r,
                               double theta, double a);
 

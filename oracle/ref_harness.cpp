@@ -8,7 +8,7 @@
 //   PointSource<double>        pointsource.h:24,   pointsource.cpp:11-64
 //   ImagePlane<double>         imageplane.h:27,    imageplane.cpp:11-121
 //   ImagePlaneBundles<double>  imageplane_bundles.h:140-181
-//   Raytracer<double>::run_raytrace (both overloads)   raytracer.cpp:63-127, 972-1034
+//   Raytracer<double>::run_raytrace (both overloads, with and without an outfile)   raytracer.cpp:63-127, 972-1034
 //   redshift_start / redshift / range_phi              raytracer.cpp:342-622
 //   FlatDisc / DiscWithISCO / FlatPlane destinations   ray_destination.h:85-204
 //   kerr_horizon / kerr_isco / integrate_disc_area     kerr.h:13-32, disc.h:125-141
@@ -145,6 +145,32 @@ void ref_run_thetalim(void* hv, int method, double theta_max, double r_max, int 
     h->base->run_raytrace(to_integrator(method), theta_max, r_max, 0, nullptr, 1, -1, -1, true, steplim);
     auto t1 = std::chrono::high_resolution_clock::now();
     h->last_trace_seconds = std::chrono::duration<double>(t1 - t0).count();
+}
+
+// run_raytrace(method, theta_max, r_max, 0, &outfile, write_step, write_rmax, write_rmin, write_cartesian, steplim): the
+// serial ray-path dumping branch (raytracer.cpp:86-100).  The text goes to `filename` through the reference's own TextOutput;
+// precision 17 makes the columns round-trip to the exact doubles (the apps use the default 8).
+void ref_run_thetalim_paths(void* hv, int method, double theta_max, double r_max, int steplim, const char* filename,
+                            int precision, int write_step, double write_rmax, double write_rmin, int write_cartesian) {
+    Quiet q;
+    Handle* h = (Handle*)hv;
+    TextOutput out(filename, false, precision, precision + 12);
+    h->base->run_raytrace(to_integrator(method), theta_max, r_max, 0, &out, write_step, write_rmax, write_rmin,
+                          write_cartesian != 0, steplim);
+    out.close();
+}
+
+void ref_run_dest_paths(void* hv, int method, int stop_kind, const double* stop_par, double r_max, int steplim,
+                        const char* filename, int precision, int write_step, double write_rmax, double write_rmin,
+                        int write_cartesian) {
+    Quiet q;
+    Handle* h = (Handle*)hv;
+    RayDestination<double>* d = make_dest(stop_kind, stop_par);
+    TextOutput out(filename, false, precision, precision + 12);
+    h->base->run_raytrace(d, to_integrator(method), r_max, 0, &out, write_step, write_rmax, write_rmin, write_cartesian != 0,
+                          steplim);
+    out.close();
+    delete d;
 }
 
 // run_raytrace(dest, method, r_max, show_progress=0, ..., steplim)        raytracer.cpp:972

@@ -89,6 +89,10 @@ class Run(C.Structure):
     ]
 
 
+class PathOpts(C.Structure):  # kt_path_opts
+    _fields_ = [("write_step", C.c_int32), ("write_cartesian", C.c_int32), ("write_rmax", C.c_double), ("write_rmin", C.c_double)]
+
+
 class PointSourceDesc(C.Structure):
     _fields_ = [
         ("pos", C.c_double * 4), ("V", C.c_double), ("E", C.c_double),
@@ -155,6 +159,27 @@ class ImageOut(C.Structure):
     ]
 
 
+class CausticCfg(C.Structure):  # kt_caustic_cfg
+    _fields_ = [
+        ("img_Nx", C.c_int32), ("img_Ny", C.c_int32),
+        ("r_isco", C.c_double), ("r_disc", C.c_double), ("dx", C.c_double), ("dy", C.c_double),
+        ("redshift_mode", C.c_int32), ("suppress", C.c_int32), ("V", C.c_double),
+    ]
+
+
+class CausticOut(C.Structure):  # kt_caustic_out
+    _fields_ = [
+        ("det_J", c_double_p), ("sign_J", c_double_p), ("order", c_int32_p), ("hit", c_int32_p),
+        ("radius", c_double_p), ("phi", c_double_p), ("x_disc", c_double_p), ("y_disc", c_double_p), ("redshift", c_double_p),
+        ("disc_count", C.c_int64), ("cnt_horizon", C.c_int64), ("cnt_rlim", C.c_int64), ("cnt_steplim", C.c_int64),
+        ("cnt_outofrange", C.c_int64), ("cnt_other", C.c_int64), ("suppressed", C.c_int64),
+        ("counters", C.c_int64 * NCOUNTERS),
+    ]
+
+
+CAUSTIC_SENTINEL = 1e30
+
+
 def dptr(a):
     """double* view of a C-contiguous float64 numpy array."""
     assert a.dtype == np.float64 and a.flags.c_contiguous
@@ -192,6 +217,33 @@ class EmisResult:
         for i in range(NCOUNTERS):
             out.c.counters[i] = int(round(packed[5 * Nr + i]))
         return out
+
+
+class CausticResult:
+    """Host-side owner of the nine maps behind a kt_caustic_out; maps are [ix, iy] like Array2D (the FITS extensions of
+    caustic_discplane.cpp:527-596 are their transposes)."""
+
+    DOUBLE_MAPS = ("det_J", "sign_J", "radius", "phi", "x_disc", "y_disc", "redshift")
+    INT_MAPS = ("order", "hit")
+    SCALARS = ("disc_count", "cnt_horizon", "cnt_rlim", "cnt_steplim", "cnt_outofrange", "cnt_other", "suppressed")
+
+    def __init__(self, nx, ny):
+        for f in self.DOUBLE_MAPS:
+            setattr(self, f, np.zeros((nx, ny)))
+        for f in self.INT_MAPS:
+            setattr(self, f, np.zeros((nx, ny), dtype=np.int32))
+        self.c = CausticOut(dptr(self.det_J), dptr(self.sign_J), self.order.ctypes.data_as(c_int32_p),
+                            self.hit.ctypes.data_as(c_int32_p), dptr(self.radius), dptr(self.phi), dptr(self.x_disc),
+                            dptr(self.y_disc), dptr(self.redshift))
+
+    def __getattr__(self, name):
+        if name in CausticResult.SCALARS:
+            return getattr(self.c, name)
+        raise AttributeError(name)
+
+    @property
+    def counters(self):
+        return np.array(list(self.c.counters), dtype=np.int64)
 
 
 class ImageResult:

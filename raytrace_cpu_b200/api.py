@@ -187,6 +187,26 @@ def make_run(method, r_max, steplim=-1, math_mode=A.MATH_EXACT, flags=0):
     return r
 
 
+class TextOutput:
+    """include/text_output.h: columns of width 20, scientific notation, 8 digits -- `setw(20) << scientific << setprecision(8)`."""
+
+    def __init__(self, filename, append=False, precision=8, colwidth=20):
+        self._own = isinstance(filename, (str, bytes)) or hasattr(filename, "__fspath__")
+        self._f = open(filename, "a" if append else "w") if self._own else filename
+        self.precision, self.width = precision, colwidth
+
+    def row(self, values):
+        self._f.write("".join(f"{v:{self.width}.{self.precision}e}" for v in values) + "\n")
+
+    def newline(self, n=1):
+        self._f.write("\n" * n)
+
+    def close(self):
+        if self._own and self._f:
+            self._f.close()
+            self._f = None
+
+
 # ---------------------------------------------------------------------------------------------------------
 # Raytracer<double>: raytracer.h:86-198
 # ---------------------------------------------------------------------------------------------------------
@@ -279,16 +299,44 @@ class Raytracer:
         for n, v in zip(names, args):
             p[n] = v
         p.update(kw)
-        if p["outfile"] is not None:
-            raise KerrtraceError("ray-path dumping (outfile) is not offloaded: reference CPU path only")
         if use_dest:
             assert p["method"] != Integrator.Euler, "Integrator::Euler does not support RayDestination stopping conditions"
             stop = p["dest"]._stop()
         else:
             stop = thetalim_stop(p["theta_max"])
         run = make_run(p["method"], p["r_max"], p["steplim"], self.math_mode)
+        if p["outfile"] is not None:
+            return self._trace_paths(stop, run, p)
         check(self.L.kt_rayset_trace(self._rs, C.byref(self._tr), C.byref(stop), C.byref(run)))
         self._dirty()
+
+    def _trace_paths(self, stop, run, p):
+        """run_raytrace with an outfile (raytracer.cpp:86-100): `outfile` is a TextOutput, a path or a writable text
+        stream.  Returns (offsets, points): ray i wrote points[offsets[i]:offsets[i + 1]], rows (t, x, y, z) or (t, r, theta, phi)."""
+        opts = A.PathOpts()
+        opts.write_step, opts.write_cartesian = int(p["write_step"]), int(bool(p["write_cartesian"]))
+        opts.write_rmax, opts.write_rmin = float(p["write_rmax"]), float(p["write_rmin"])
+        host = np.ascontiguousarray(self.rays)
+        n = self.nRays
+        before = host["steps"].copy()
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        ptr = host.ctypes.data_as(C.c_void_p)
+        args = (self.ctx.h, C.byref(self._tr), C.byref(stop), C.byref(run), ptr, n, C.byref(opts))
+        check(self.L.kt_trace_paths_count(*args, offsets.ctypes.data_as(A.c_int64_p)))
+        points = np.zeros((int(offsets[n]), 4), dtype=np.float64)
+        check(self.L.kt_trace_paths(*args, offsets.ctypes.data_as(A.c_int64_p), points.ctypes.data_as(A.c_double_p)))
+        self.upload(host)
+        steplim = run.steplim if run.steplim > 0 else (A.RK45_STEPLIM if run.integrator == A.RK45 else A.STEPLIM)
+        out = p["outfile"] if isinstance(p["outfile"], TextOutput) else TextOutput(p["outfile"])
+        for i in range(n):
+            if before[i] < 0 or before[i] >= steplim:      # skipped rays write nothing, not even the blank lines
+                continue
+            for row in points[offsets[i]:offsets[i + 1]]:
+                out.row(row)
+            out.newline(2)
+        if out is not p["outfile"]:
+            out.close()
+        return offsets, points
 
     def redshift_start(self, V, reverse=False, projradius=False):
         check(self.L.kt_rayset_redshift_start(self._rs, C.byref(self._tr), V, int(reverse), int(projradius)))
@@ -539,4 +587,34 @@ def plane_rays(plane, spin, stop, method=Integrator.RK4, r_max=None, precision=A
     out = np.zeros(n, dtype=A.RAY_MIN_DTYPE)
     check(ctx.L.kt_imageplane_rays(ctx.h, C.byref(plane), C.byref(tr), C.byref(stop), C.byref(run), redshift_mode, V,
                                    int(range_phi), out.ctypes.data_as(C.c_void_p), n))
+    return out
+
+
+def caustic_discplane(dist, incl, spin, r_disc, Nx, Ny=None, x0=None, xmax=None, y0=None, ymax=None, plane_phi0=0.0,
+                      method=Integrator.RK45, rk45_tol=1e-8, precision=A.PRECISION, bundle_eps_frac=0.01, suppress=True,
+                      steplim=-1, ctx=None, math_mode=A.MATH_EXACT):
+    """The whole of caustic_discplane.cpp:56-493 with its par-file parameter names: an (Nx + 1) x (Ny + 1) image plane (ray
+    bundles when bundle_eps_frac > 0, else single rays and grid-neighbour differences) traced to the disc annulus
+    [r_isco, r_disc] with DiscWithISCODestination, redshift(dest, reverse), the nine per-pixel maps, the Jacobian determinant
+    of the lens mapping and the suppression pass -- one C ABI call, everything on the device.  -> A.CausticResult"""
+    ctx = ctx or get_context()
+    x0 = -1 * r_disc if x0 is None else x0
+    xmax = r_disc if xmax is None else xmax
+    y0 = x0 if y0 is None else y0
+    ymax = xmax if ymax is None else ymax
+    Ny = Nx if Ny is None else Ny
+    dx, dy = (xmax - x0) / Nx, (ymax - y0) / Ny
+    use_bundles = bundle_eps_frac > 0.0
+    plane = imageplane_desc(dist, incl, x0, xmax, dx, y0, ymax, dy, plane_phi0, use_bundles, bundle_eps_frac if use_bundles else 0.01)
+    r_isco = kerr_isco(spin, +1)
+    tr = make_tracer(-1 * spin, precision)
+    tr.rk45_tol = rk45_tol
+    stop = DiscWithISCODestination(r_isco, r_disc)._stop()
+    run = make_run(method, 1.1 * dist, steplim, math_mode)
+    cfg = A.CausticCfg()
+    cfg.img_Nx, cfg.img_Ny = Nx + 1, Ny + 1
+    cfg.r_isco, cfg.r_disc, cfg.dx, cfg.dy = r_isco, r_disc, dx, dy
+    cfg.redshift_mode, cfg.suppress, cfg.V = A.REDSHIFT_DEST, int(suppress), -1.0
+    out = A.CausticResult(Nx + 1, Ny + 1)
+    check(ctx.L.kt_caustic_discplane(ctx.h, C.byref(plane), C.byref(tr), C.byref(stop), C.byref(run), C.byref(cfg), C.byref(out.c)))
     return out

@@ -10,6 +10,7 @@
 #include "kt_types.h"
 #include "kt_kernels.h"
 
+using kt::CausticMaps;
 using kt::KernelTable;
 using kt::LaunchCfg;
 using kt::PlaneFrame;
@@ -65,6 +66,8 @@ struct kt_ctx {
     unsigned long long* d_pipe_queue = nullptr;   // NPIPE counters
     double* d_pipe_cnt = nullptr;                 // NPIPE x KT_NCOUNTERS
     long long pipe_chunk = 1ll << 40;             // rays per chunk: default = no chunking (see kt_trace); KT_PIPE_CHUNK overrides
+    int carveout = -1;                            // KT_CARVEOUT: preferred shared-memory carve-out of the trace kernels (percent)
+    int zerocopy = 1;                             // kt_trace on pinned host arrays: kernel addresses them directly (KT_ZEROCOPY=0: staged)
 };
 
 struct kt_rayset {
@@ -166,6 +169,10 @@ extern "C" kt_ctx* kt_create(int device)
     c->timeout_s = to ? atof(to) : 0;
     const char* pc = getenv("KT_PIPE_CHUNK");
     if (pc && atoll(pc) > 0) c->pipe_chunk = atoll(pc);
+    const char* co = getenv("KT_CARVEOUT");
+    if (co) c->carveout = atoi(co);
+    const char* zc = getenv("KT_ZEROCOPY");
+    if (zc) c->zerocopy = atoi(zc) != 0;
     bool pipe_ok = cudaEventCreateWithFlags(&c->pipe_start, cudaEventDisableTiming) == cudaSuccess &&
                    cudaMalloc(&c->d_pipe_queue, kt_ctx::NPIPE * sizeof(unsigned long long)) == cudaSuccess &&
                    cudaMalloc(&c->d_pipe_cnt, kt_ctx::NPIPE * KT_NCOUNTERS * sizeof(double)) == cudaSuccess;
@@ -271,6 +278,7 @@ static LaunchCfg cfg_of(kt_ctx* c)
     cfg.stream = c->stream;
     cfg.sm_count = c->sm_count;
     cfg.min_blocks = c->min_blocks;
+    cfg.carveout = c->carveout;
     return cfg;
 }
 
@@ -335,9 +343,11 @@ static int make_params(TraceParams& P, const kt_tracer* tr, const kt_stop* stop,
     P.tr = *tr;
     if (stop) P.stop = *stop;
     if (run) {
-        if (run->integrator == KT_EULER)
-            return fail(KT_ERR_UNSUPPORTED, "Integrator::Euler is not offloaded (reference CPU path only)");
-        if (run->integrator != KT_RK4 && run->integrator != KT_RK45) return fail(KT_ERR_INVALID, "unknown integrator %d", run->integrator);
+        if (run->integrator != KT_EULER && run->integrator != KT_RK4 && run->integrator != KT_RK45)
+            return fail(KT_ERR_INVALID, "unknown integrator %d", run->integrator);
+        // the reference asserts this (raytracer.cpp:983): Euler only exists for the theta_max overload
+        if (run->integrator == KT_EULER && stop && stop->kind != KT_STOP_THETALIM)
+            return fail(KT_ERR_INVALID, "Integrator::Euler does not support RayDestination stopping conditions");
         P.integrator = run->integrator;
         P.rlim = run->r_max;
         P.steplim = run->steplim > 0 ? run->steplim : (run->integrator == KT_RK45 ? KT_RK45_STEPLIM : KT_STEPLIM); // raytracer.cpp:80
@@ -736,11 +746,34 @@ static int stage_out(kt_ctx* c, kt_ray* rays, int64_t n)
 extern "C" int kt_trace(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, const kt_run* run, kt_ray* rays, int64_t n)
 {
     if (!stop || !run) return fail(KT_ERR_INVALID, "null stop / run");
-    if (int rc = stage_in(c, rays, n, false)) return rc;
+    if (!rays || n < 0) return fail(KT_ERR_INVALID, "bad ray buffer");
+    if (int rc = ctx_bind(c)) return rc;
     if (n == 0) return KT_OK;
     TraceParams P0;
     if (int rc = make_params(P0, tr, stop, run)) return rc;
     const KernelTable* T = table_for(run->math_mode);
+    // Zero-copy: when the application's array is pinned host memory the device can address (kt_host_alloc, which is what
+    // the shim's Raytracer::rays uses, or any cudaHostAlloc / cudaHostRegister'ed buffer), the persistent kernel reads each
+    // ray's record over PCIe when a lane picks the ray up and writes the result record back when the ray retires: the
+    // transfers hide completely under the integration (144 B in + 88 B out against ~1.4e5 flop per ray) and no device
+    // staging copy exists.  KT_ZEROCOPY=0 forces the staged H2D -> kernel -> D2H path.
+    if (c->zerocopy) {
+        cudaPointerAttributes pa;
+        memset(&pa, 0, sizeof(pa));
+        if (cudaPointerGetAttributes(&pa, rays) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
+            TraceParams P = P0;
+            set_work(P, c, n, nullptr);
+            if (int rc = ensure_scratch(c, KT_NCOUNTERS * sizeof(double))) return rc;
+            KT_CUDA(cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned long long), c->stream));
+            KT_CUDA(cudaMemsetAsync(c->d_scratch, 0, KT_NCOUNTERS * sizeof(double), c->stream));
+            KT_CUDA(T->trace_rayset(cfg_of(c), P, static_cast<kt_ray*>(pa.devicePointer), c->d_scratch));
+            c->launches++;
+            KT_CUDA(cudaStreamSynchronize(c->stream));
+            return c->timeout_s > 0 ? kt_aborted(c) : KT_OK;
+        }
+        cudaGetLastError();   // not a CUDA-visible pointer: staged path
+    }
+    if (int rc = stage_in(c, rays, n, false)) return rc;
     KT_CUDA(cudaEventRecord(c->pipe_start, c->stream));
     for (int i = 0; i < kt_ctx::NPIPE; i++) KT_CUDA(cudaStreamWaitEvent(c->pipe[i], c->pipe_start, 0));
     KT_CUDA(cudaMemsetAsync(c->d_pipe_cnt, 0, kt_ctx::NPIPE * KT_NCOUNTERS * sizeof(double), c->pipe[0]));
@@ -789,6 +822,87 @@ extern "C" int kt_trace(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, con
     }
     return c->timeout_s > 0 ? kt_aborted(c) : KT_OK;
 }
+// ---------------------------------------------------------------------------------------------------------
+// ray-path dumping (run_raytrace with an outfile, raytracer.cpp:86-100 / 995-1008): counting pass, then writing pass
+// ---------------------------------------------------------------------------------------------------------
+static int check_path_args(const kt_stop* stop, const kt_run* run, const kt_ray* rays, int64_t n, const kt_path_opts* o)
+{
+    if (!stop || !run || !o) return fail(KT_ERR_INVALID, "null stop / run / path options");
+    if (!rays || n < 0) return fail(KT_ERR_INVALID, "bad ray buffer");
+    if (o->write_step <= 0) return fail(KT_ERR_INVALID, "write_step must be positive");
+    return KT_OK;
+}
+
+struct DevBuf {   // scoped device allocation
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes)
+    {
+        if (cudaMalloc(&p, bytes ? bytes : 8) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            return fail(KT_ERR_NOMEM, "device allocation of %zu bytes failed", bytes);
+        }
+        return KT_OK;
+    }
+};
+
+static int run_paths(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, const kt_run* run, const kt_ray* rays, int64_t n,
+                     const kt_path_opts* o, long long* d_counts, const long long* d_offsets, double* d_points)
+{
+    TraceParams P;
+    if (int rc = make_params(P, tr, stop, run)) return rc;
+    if (int rc = ensure_rays(c, (size_t)n * sizeof(kt_ray))) return rc;
+    if (int rc = ensure_scratch(c, KT_NCOUNTERS * sizeof(double))) return rc;
+    KT_CUDA(cudaMemcpyAsync(c->d_rays, rays, (size_t)n * sizeof(kt_ray), cudaMemcpyHostToDevice, c->stream));
+    set_work(P, c, n, nullptr);
+    KT_CUDA(cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned long long), c->stream));
+    KT_CUDA(cudaMemsetAsync(c->d_scratch, 0, KT_NCOUNTERS * sizeof(double), c->stream));
+    KT_CUDA(table_for(run->math_mode)->trace_paths(cfg_of(c), P, c->d_rays, c->d_scratch, *o, d_counts, d_offsets, d_points));
+    c->launches++;
+    return KT_OK;
+}
+
+extern "C" int kt_trace_paths_count(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, const kt_run* run, const kt_ray* rays,
+                                    int64_t n, const kt_path_opts* o, int64_t* offsets)
+{
+    if (int rc = check_path_args(stop, run, rays, n, o)) return rc;
+    if (!offsets) return fail(KT_ERR_INVALID, "null offsets");
+    if (int rc = ctx_bind(c)) return rc;
+    offsets[0] = 0;
+    if (n == 0) return KT_OK;
+    DevBuf counts;
+    if (int rc = counts.alloc((size_t)n * sizeof(long long))) return rc;
+    KT_CUDA(cudaMemsetAsync(counts.p, 0, (size_t)n * sizeof(long long), c->stream));   // skipped rays write no points
+    if (int rc = run_paths(c, tr, stop, run, rays, n, o, static_cast<long long*>(counts.p), nullptr, nullptr)) return rc;
+    // counts land in offsets[1..n], then an in-place inclusive scan turns them into exclusive prefix sums
+    KT_CUDA(cudaMemcpyAsync(offsets + 1, counts.p, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    for (int64_t i = 1; i <= n; i++) offsets[i] += offsets[i - 1];
+    return c->timeout_s > 0 ? kt_aborted(c) : KT_OK;
+}
+
+extern "C" int kt_trace_paths(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, const kt_run* run, kt_ray* rays, int64_t n,
+                              const kt_path_opts* o, const int64_t* offsets, double* points)
+{
+    if (int rc = check_path_args(stop, run, rays, n, o)) return rc;
+    if (!offsets) return fail(KT_ERR_INVALID, "null offsets");
+    if (int rc = ctx_bind(c)) return rc;
+    if (n == 0) return KT_OK;
+    const long long total = offsets[n];
+    if (total < 0 || (total > 0 && !points)) return fail(KT_ERR_INVALID, "bad offsets / null points");
+    DevBuf d_off, d_pts;
+    if (int rc = d_off.alloc((size_t)(n + 1) * sizeof(long long))) return rc;
+    if (int rc = d_pts.alloc((size_t)total * 4 * sizeof(double))) return rc;
+    KT_CUDA(cudaMemcpyAsync(d_off.p, offsets, (size_t)(n + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    if (int rc = run_paths(c, tr, stop, run, rays, n, o, nullptr, static_cast<const long long*>(d_off.p), static_cast<double*>(d_pts.p)))
+        return rc;
+    KT_CUDA(cudaMemcpyAsync(rays, c->d_rays, (size_t)n * sizeof(kt_ray), cudaMemcpyDeviceToHost, c->stream));
+    if (total > 0) KT_CUDA(cudaMemcpyAsync(points, d_pts.p, (size_t)total * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    return c->timeout_s > 0 ? kt_aborted(c) : KT_OK;
+}
+
 extern "C" int kt_redshift_start(kt_ctx* c, const kt_tracer* tr, kt_ray* rays, int64_t n, double V, int reverse, int projradius)
 {
     if (int rc = stage_in(c, rays, n, true)) return rc;
@@ -888,6 +1002,84 @@ extern "C" int kt_imageplane_image(kt_ctx* c, const kt_imageplane* p, const kt_t
     KT_CUDA(cudaMemsetAsync(c->d_scratch, 0, nd * sizeof(double), c->stream));
     if (int rc = kt_imageplane_image_dev(c, p, tr, stop, run, b, sh, c->d_scratch)) return rc;
     return fetch_image(c, c->d_scratch, npix, out);
+}
+
+// image plane (or bundles) -> trace -> redshift: compact per-ray results left in c->d_rays (count slots, the first
+// Nx * Ny * (bundles ? 5 : 1) of them live)
+static int dev_plane_rays(kt_ctx* c, const kt_imageplane* p, const kt_tracer* tr, const kt_stop* stop, const kt_run* run,
+                          int redshift_mode, double V, int range_phi, PlaneFrame& F, long long count)
+{
+    TraceParams P;
+    if (int rc = make_params(P, tr, stop, run)) return rc;
+    make_plane_frame(F, p);
+    set_work(P, c, count, nullptr);
+    kt_image_bins B;
+    memset(&B, 0, sizeof(B));
+    B.redshift_mode = redshift_mode;
+    B.reverse = 1;
+    B.V = V;
+    const size_t out_bytes = (size_t)count * sizeof(kt_ray_min);
+    if (int rc = ensure_rays(c, out_bytes + KT_NCOUNTERS * sizeof(double))) return rc;
+    kt_ray_min* d_out = reinterpret_cast<kt_ray_min*>(c->d_rays);
+    double* d_cnt = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(c->d_rays) + out_bytes);
+    KT_CUDA(cudaMemsetAsync(d_out, 0, out_bytes + KT_NCOUNTERS * sizeof(double), c->stream));
+    KT_CUDA(cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned long long), c->stream));
+    KT_CUDA(table_for(run->math_mode)->trace_planerays(cfg_of(c), P, F, B, range_phi, d_out, d_cnt));
+    c->launches++;
+    return KT_OK;
+}
+
+extern "C" int kt_caustic_discplane(kt_ctx* c, const kt_imageplane* p, const kt_tracer* tr, const kt_stop* stop, const kt_run* run,
+                                    const kt_caustic_cfg* cfg, kt_caustic_out* out)
+{
+    if (int rc = ctx_bind(c)) return rc;
+    if (!p || !stop || !run || !cfg || !out) return fail(KT_ERR_INVALID, "bad arguments");
+    if (cfg->img_Nx <= 0 || cfg->img_Ny <= 0) return fail(KT_ERR_INVALID, "bad map size %d x %d", cfg->img_Nx, cfg->img_Ny);
+    const long long count = kt_imageplane_count(p, nullptr, nullptr);
+    const long long npix = (long long)cfg->img_Nx * cfg->img_Ny;
+    PlaneFrame F;
+    if (count > 0) {
+        if (int rc = dev_plane_rays(c, p, tr, stop, run, cfg->redshift_mode, cfg->V, 0, F, count)) return rc;
+    } else {
+        make_plane_frame(F, p);
+    }
+    const long long live = (long long)F.Nx * F.Ny * (F.bundles ? 5 : 1);
+    // one allocation: 8 double maps (the 7 outputs + the sign snapshot), 2 int maps, 7 counters
+    DevBuf buf;
+    const size_t bytes = (size_t)npix * (8 * sizeof(double) + 2 * sizeof(int)) + 8 * sizeof(unsigned long long);
+    if (int rc = buf.alloc(bytes)) return rc;
+    KT_CUDA(cudaMemsetAsync(buf.p, 0, bytes, c->stream));
+    CausticMaps m;
+    double* dp = static_cast<double*>(buf.p);
+    m.det_J = dp; m.sign_J = dp + npix; m.radius = dp + 2 * npix; m.phi = dp + 3 * npix; m.x_disc = dp + 4 * npix;
+    m.y_disc = dp + 5 * npix; m.redshift = dp + 6 * npix; m.sign_snap = dp + 7 * npix;
+    m.cnt = reinterpret_cast<unsigned long long*>(dp + 8 * npix);
+    m.order = reinterpret_cast<int*>(m.cnt + 8);
+    m.hit = m.order + npix;
+    const KernelTable* T = kt_kernel_table_exact();
+    const kt_ray_min* d_rays = reinterpret_cast<const kt_ray_min*>(c->d_rays);
+    for (int pass = 0; pass < (cfg->suppress ? 3 : 2); pass++) {
+        KT_CUDA(T->caustic_pass(cfg_of(c), pass, d_rays, count > 0 ? live : 0, (int)F.Ny, F.bundles, F.eps_x, F.eps_y, *cfg, m));
+        c->launches++;
+    }
+    struct { void* dst; const void* src; size_t n; } copies[] = {
+        {out->det_J, m.det_J, sizeof(double)}, {out->sign_J, m.sign_J, sizeof(double)}, {out->radius, m.radius, sizeof(double)},
+        {out->phi, m.phi, sizeof(double)}, {out->x_disc, m.x_disc, sizeof(double)}, {out->y_disc, m.y_disc, sizeof(double)},
+        {out->redshift, m.redshift, sizeof(double)}, {out->order, m.order, sizeof(int)}, {out->hit, m.hit, sizeof(int)}};
+    for (auto& cp : copies)
+        if (cp.dst) KT_CUDA(cudaMemcpyAsync(cp.dst, cp.src, (size_t)npix * cp.n, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long cnt[8];
+    KT_CUDA(cudaMemcpyAsync(cnt, m.cnt, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+    double tc[KT_NCOUNTERS] = {0};
+    if (count > 0)
+        KT_CUDA(cudaMemcpyAsync(tc, reinterpret_cast<unsigned char*>(c->d_rays) + (size_t)count * sizeof(kt_ray_min), sizeof(tc),
+                                cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    out->disc_count = (int64_t)cnt[0]; out->cnt_horizon = (int64_t)cnt[1]; out->cnt_rlim = (int64_t)cnt[2];
+    out->cnt_steplim = (int64_t)cnt[3]; out->cnt_outofrange = (int64_t)cnt[4]; out->cnt_other = (int64_t)cnt[5];
+    out->suppressed = (int64_t)cnt[6];
+    unpack_counters(tc, out->counters);
+    return c->timeout_s > 0 ? kt_aborted(c) : KT_OK;
 }
 
 extern "C" int kt_imageplane_rays(kt_ctx* c, const kt_imageplane* p, const kt_tracer* tr, const kt_stop* stop, const kt_run* run,
@@ -1001,5 +1193,8 @@ extern "C" int kt_abi_sizeof(const char* name)
     if (!strcmp(name, "kt_emis_out")) return (int)sizeof(kt_emis_out);
     if (!strcmp(name, "kt_image_bins")) return (int)sizeof(kt_image_bins);
     if (!strcmp(name, "kt_image_out")) return (int)sizeof(kt_image_out);
+    if (!strcmp(name, "kt_path_opts")) return (int)sizeof(kt_path_opts);
+    if (!strcmp(name, "kt_caustic_cfg")) return (int)sizeof(kt_caustic_cfg);
+    if (!strcmp(name, "kt_caustic_out")) return (int)sizeof(kt_caustic_out);
     return -1;
 }

@@ -12,7 +12,16 @@ namespace KT_MODE_NS {
 // IO policy 1: device-resident AoS ray set in, same ray set out  (Raytracer<T>::run_raytrace on `rays`)
 // =========================================================================================================
 struct RaysetIO {
-    static constexpr int ND_IN = 12, NI_IN = 8, ND_OUT = 8, NI_OUT = 9;
+    // Retirement is a handful of stores, so it runs from the lane (no outbox); the inbox carries pr / ptheta only
+    // because a theta turning point on a ray's very first step leaves them as they were (raytracer.cpp:824-829).  Small
+    // staging matters in the exact mode: its spills live in L1, which is what shared memory leaves over.
+    static constexpr int ND_IN = 10, NI_IN = 8, ND_OUT = 0, NI_OUT = 0;
+    static constexpr bool DIRECT_RETIRE = true;
+    static constexpr bool KEEP_MOM = true;     // Ray::pt..pphi are written back (raytracer.cpp:956-959)
+    static constexpr bool PATHS = false;
+    template <class H> __device__ void setup_paths(H&) {}
+    __device__ long long path_first(long long) { return 0; }
+    __device__ void path_done(long long, int) {}
     kt_ray* rays;
     double* counters;
     unsigned char* smem;
@@ -39,8 +48,7 @@ struct RaysetIO {
     {
         b.d[0][slot] = in.t; b.d[1][slot] = in.r; b.d[2][slot] = in.th; b.d[3][slot] = in.ph;
         b.d[4][slot] = in.k; b.d[5][slot] = in.h; b.d[6][slot] = in.Q;
-        b.d[7][slot] = in.pt; b.d[8][slot] = in.pr; b.d[9][slot] = in.pth; b.d[10][slot] = in.pph;
-        b.d[11][slot] = in.step0;
+        b.d[7][slot] = in.pr; b.d[8][slot] = in.pth; b.d[9][slot] = in.step0;
         b.i[0][slot] = (int)(in.idx & 0xffffffffll); b.i[1][slot] = (int)(in.idx >> 32);
         b.i[2][slot] = in.steps0; b.i[3][slot] = in.status0; b.i[4][slot] = in.sr; b.i[5][slot] = in.sth;
         b.i[6][slot] = in.flips; b.i[7][slot] = in.cross;
@@ -49,29 +57,15 @@ struct RaysetIO {
     {
         in.t = b.d[0][slot]; in.r = b.d[1][slot]; in.th = b.d[2][slot]; in.ph = b.d[3][slot];
         in.k = b.d[4][slot]; in.h = b.d[5][slot]; in.Q = b.d[6][slot];
-        in.pt = b.d[7][slot]; in.pr = b.d[8][slot]; in.pth = b.d[9][slot]; in.pph = b.d[10][slot];
-        in.step0 = b.d[11][slot];
+        in.pt = 0; in.pr = b.d[7][slot]; in.pth = b.d[8][slot]; in.pph = 0;   // pt / pphi: rewritten by the first step
+        in.step0 = b.d[9][slot];
         in.idx = ((long long)b.i[1][slot] << 32) | (unsigned int)b.i[0][slot];
         in.steps0 = b.i[2][slot]; in.status0 = b.i[3][slot]; in.sr = b.i[4][slot]; in.sth = b.i[5][slot];
         in.flips = b.i[6][slot]; in.cross = b.i[7][slot];
         in.emit = 0; in.alpha = 0; in.beta = 0;
     }
-    __device__ void pack_out(Stage<ND_OUT, NI_OUT>& b, int slot, const RayOut& o)
-    {
-        b.d[0][slot] = o.t; b.d[1][slot] = o.r; b.d[2][slot] = o.th; b.d[3][slot] = o.ph;
-        b.d[4][slot] = o.pt; b.d[5][slot] = o.pr; b.d[6][slot] = o.pth; b.d[7][slot] = o.pph;
-        b.i[0][slot] = (int)(o.idx & 0xffffffffll); b.i[1][slot] = (int)(o.idx >> 32);
-        b.i[2][slot] = o.steps0; b.i[3][slot] = o.steps; b.i[4][slot] = o.status; b.i[5][slot] = o.sr;
-        b.i[6][slot] = o.sth; b.i[7][slot] = o.flips; b.i[8][slot] = o.cross;
-    }
-    __device__ void unpack_out(const Stage<ND_OUT, NI_OUT>& b, int slot, RayOut& o)
-    {
-        o.t = b.d[0][slot]; o.r = b.d[1][slot]; o.th = b.d[2][slot]; o.ph = b.d[3][slot];
-        o.pt = b.d[4][slot]; o.pr = b.d[5][slot]; o.pth = b.d[6][slot]; o.pph = b.d[7][slot];
-        o.idx = ((long long)b.i[1][slot] << 32) | (unsigned int)b.i[0][slot];
-        o.steps0 = b.i[2][slot]; o.steps = b.i[3][slot]; o.status = b.i[4][slot]; o.sr = b.i[5][slot];
-        o.sth = b.i[6][slot]; o.flips = b.i[7][slot]; o.cross = b.i[8][slot];
-    }
+    __device__ void pack_out(Stage<ND_OUT, NI_OUT>&, int, const RayOut&) {}      // unused: DIRECT_RETIRE
+    __device__ void unpack_out(const Stage<ND_OUT, NI_OUT>&, int, RayOut&) {}
     // write-back: raytracer.cpp:952-967
     __device__ void retire(const TraceParams&, const RayOut& o, LaneCounters& c)
     {
@@ -86,6 +80,22 @@ struct RaysetIO {
         q.steps = st;
         count_terminal(c, o.steps, o.status);
     }
+};
+
+// =========================================================================================================
+// IO policy 1b: the same ray set, dumping ray paths  (run_raytrace with an outfile: raytracer.cpp:86-100)
+//   points == nullptr: counting pass, counts[idx] = number of points ray idx writes
+//   points != nullptr: writing pass, ray idx writes its points from offsets[idx] on
+// =========================================================================================================
+struct PathIO : RaysetIO {
+    static constexpr bool PATHS = true;
+    kt_path_opts opts;
+    long long* counts;
+    const long long* offsets;
+    double* points;
+    template <class H> __device__ void setup_paths(H& h) { h.opts = opts; h.points = points; }
+    __device__ long long path_first(long long idx) { return points ? offsets[idx] : 0; }
+    __device__ void path_done(long long idx, int npts) { if (!points) counts[idx] = npts; }
 };
 
 // =========================================================================================================
@@ -106,6 +116,12 @@ __device__ __forceinline__ int final_steps(int steps, int status)
 // =========================================================================================================
 struct EmisIO {
     static constexpr int ND_IN = 5, NI_IN = 3, ND_OUT = 7, NI_OUT = 3;
+    static constexpr bool DIRECT_RETIRE = false;
+    static constexpr bool KEEP_MOM = false;
+    static constexpr bool PATHS = false;
+    template <class H> __device__ void setup_paths(H&) {}
+    __device__ long long path_first(long long) { return 0; }
+    __device__ void path_done(long long, int) {}
     PointSourceFrame F;
     kt_emis_bins B;
     double log_dr;     // log(dr) evaluated by the host libm
@@ -217,6 +233,12 @@ struct EmisIO {
 template <bool IMAGE>
 struct PlaneIO {
     static constexpr int ND_IN = 7, NI_IN = 3, ND_OUT = 7, NI_OUT = 7;
+    static constexpr bool DIRECT_RETIRE = false;
+    static constexpr bool KEEP_MOM = false;
+    static constexpr bool PATHS = false;
+    template <class H> __device__ void setup_paths(H&) {}
+    __device__ long long path_first(long long) { return 0; }
+    __device__ void path_done(long long, int) {}
     PlaneFrame F;
     kt_image_bins B;      // IMAGE only (redshift_mode / reverse / V also used by the ray variant)
     double* maps;         // IMAGE: double[7*npix + KT_NCOUNTERS]
@@ -504,6 +526,146 @@ __global__ void k_bin_image(const kt_ray* rays, long long n, kt_image_bins B, do
     flush_counters(c, maps + 7 * npix);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// caustic / critical-curve maps (caustic_discplane.cpp:146-493), one thread per pixel, on the compact per-ray results the
+// plane kernel left in HBM.  Rays beyond n_live (surplus tail slots) read as unused (steps = -1).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ kt_ray_min caustic_ray(const kt_ray_min* rays, long long n_live, long long idx)
+{
+    if (idx < n_live) return rays[idx];
+    kt_ray_min u = {};
+    u.steps = -1;
+    return u;
+}
+__device__ __forceinline__ bool caustic_valid_hit(const kt_ray_min& q, const kt_caustic_cfg& c)   // caustic_discplane.cpp:177-182
+{
+    return q.steps > 0 && q.r >= c.r_isco && q.r < c.r_disc && q.redshift > 0;
+}
+__device__ __forceinline__ void caustic_disc_xy(double phi_acc, double r, double& xd, double& yd)   // caustic_discplane.cpp:170-174
+{
+    const double phi_s = atan2(sin(phi_acc), cos(phi_acc));
+    xd = r * cos(phi_s);
+    yd = r * sin(phi_s);
+}
+
+// centre rays -> the seven per-pixel maps + the app's diagnostic counts: caustic_discplane.cpp:220-274 / 351-406
+__global__ void k_caustic_centres(const kt_ray_min* rays, long long n_live, int plane_Ny, int per, kt_caustic_cfg c, CausticMaps m)
+{
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= (long long)c.img_Nx * c.img_Ny) return;
+    const int ix = (int)(p / c.img_Ny), iy = (int)(p - (long long)ix * c.img_Ny);
+    const kt_ray_min q = caustic_ray(rays, n_live, ((long long)ix * plane_Ny + iy) * per);
+    if (caustic_valid_hit(q, c)) {
+        const double phi_s = atan2(sin(q.phi), cos(q.phi));
+        const int phi_ord = (int)(fabs(q.phi) / (2 * KT_PI)), r_ord = q.rdot_flips / 2;
+        m.hit[p] = 1;
+        m.radius[p] = q.r;
+        m.phi[p] = phi_s;
+        m.x_disc[p] = q.r * cos(phi_s);
+        m.y_disc[p] = q.r * sin(phi_s);
+        m.order[p] = phi_ord > r_ord ? phi_ord : r_ord;
+        m.redshift[p] = q.redshift;
+        atomicAdd(&m.cnt[0], 1ull);
+    } else {
+        m.hit[p] = 0;
+        m.radius[p] = 0; m.phi[p] = 0; m.x_disc[p] = 0; m.y_disc[p] = 0; m.redshift[p] = 0;
+        m.order[p] = -1;
+    }
+    if (q.steps > 0 && (q.r < c.r_isco || q.r >= c.r_disc || q.redshift <= 0)) atomicAdd(&m.cnt[4], 1ull);
+    else if (q.steps <= 0 || !(q.status & KT_STATUS_DEST)) {
+        if (q.status & KT_STATUS_HORIZON) atomicAdd(&m.cnt[1], 1ull);
+        else if (q.status & KT_STATUS_RLIM) atomicAdd(&m.cnt[2], 1ull);
+        else if (q.status & KT_STATUS_STEPLIM) atomicAdd(&m.cnt[3], 1ull);
+        else atomicAdd(&m.cnt[5], 1ull);
+    }
+}
+
+// Jacobian determinant of (x, y) -> (x_disc, y_disc): from the four satellite rays of the bundle
+// (caustic_discplane.cpp:277-333) or from the four grid neighbours (caustic_discplane.cpp:409-447)
+__global__ void k_caustic_jacobian(const kt_ray_min* rays, long long n_live, int plane_Ny, int bundles, double eps_x, double eps_y,
+                                   kt_caustic_cfg c, CausticMaps m)
+{
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= (long long)c.img_Nx * c.img_Ny) return;
+    const int Nx = c.img_Nx, Ny = c.img_Ny;
+    const int ix = (int)(p / Ny), iy = (int)(p - (long long)ix * Ny);
+    double det = __longlong_as_double(0x7ff8000000000000ll);   // quiet NaN: undefined
+    double sgn = 0;
+    bool defined = false;
+    if (m.hit[p]) {
+        if (bundles) {
+            const long long base = ((long long)ix * plane_Ny + iy) * 5;
+            const kt_ray_min rc = caustic_ray(rays, n_live, base), re = caustic_ray(rays, n_live, base + 1),
+                             rw = caustic_ray(rays, n_live, base + 2), rn = caustic_ray(rays, n_live, base + 3),
+                             rs = caustic_ray(rays, n_live, base + 4);
+            if (caustic_valid_hit(re, c) && caustic_valid_hit(rw, c) && caustic_valid_hit(rn, c) && caustic_valid_hit(rs, c)) {
+                const int flips = rc.rdot_flips;
+                const double phi_c = rc.phi;
+                const bool match = re.rdot_flips == flips && rw.rdot_flips == flips && rn.rdot_flips == flips &&
+                                   rs.rdot_flips == flips && fabs(re.phi - phi_c) < KT_PI_2 && fabs(rw.phi - phi_c) < KT_PI_2 &&
+                                   fabs(rn.phi - phi_c) < KT_PI_2 && fabs(rs.phi - phi_c) < KT_PI_2;
+                if (!match) {
+                    det = KT_CAUSTIC_SENTINEL;
+                } else {
+                    double xe, ye, xw, yw, xn, yn, xs, ys;
+                    caustic_disc_xy(re.phi, re.r, xe, ye);
+                    caustic_disc_xy(rw.phi, rw.r, xw, yw);
+                    caustic_disc_xy(rn.phi, rn.r, xn, yn);
+                    caustic_disc_xy(rs.phi, rs.r, xs, ys);
+                    const double dxd_da = (xe - xw) / (2 * eps_x), dxd_db = (xn - xs) / (2 * eps_y);
+                    const double dyd_da = (ye - yw) / (2 * eps_x), dyd_db = (yn - ys) / (2 * eps_y);
+                    det = __dsub_rn(__dmul_rn(dxd_da, dyd_db), __dmul_rn(dxd_db, dyd_da));
+                    defined = true;
+                }
+            }
+        } else if (!(ix == 0 || ix == Nx - 1 || iy == 0 || iy == Ny - 1)) {
+            const long long e = p + Ny, w = p - Ny, nn = p + 1, ss = p - 1;
+            if (m.hit[e] && m.hit[w] && m.hit[nn] && m.hit[ss]) {
+                const int ord = m.order[p];
+                if (!(m.order[e] == ord && m.order[w] == ord && m.order[nn] == ord && m.order[ss] == ord)) {
+                    det = KT_CAUSTIC_SENTINEL;
+                } else {
+                    const double dxd_dx = (m.x_disc[e] - m.x_disc[w]) / (2 * c.dx), dxd_dy = (m.x_disc[nn] - m.x_disc[ss]) / (2 * c.dy);
+                    const double dyd_dx = (m.y_disc[e] - m.y_disc[w]) / (2 * c.dx), dyd_dy = (m.y_disc[nn] - m.y_disc[ss]) / (2 * c.dy);
+                    det = __dsub_rn(__dmul_rn(dxd_dx, dyd_dy), __dmul_rn(dxd_dy, dyd_dx));
+                    defined = true;
+                }
+            }
+        }
+    }
+    if (defined) sgn = (det > 0) ? 1.0 : (det < 0) ? -1.0 : 0.0;
+    m.det_J[p] = det;
+    m.sign_J[p] = sgn;
+    m.sign_snap[p] = sgn;
+}
+
+// suppression of alternating-sign pixels at geodesic branch boundaries, on the snapshot: caustic_discplane.cpp:467-492
+__global__ void k_caustic_suppress(kt_caustic_cfg c, CausticMaps m)
+{
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= (long long)c.img_Nx * c.img_Ny) return;
+    const int Nx = c.img_Nx, Ny = c.img_Ny;
+    const int ix = (int)(p / Ny), iy = (int)(p - (long long)ix * Ny);
+    const double s = m.sign_snap[p];
+    if (s == 0.0) return;
+    int n_same = 0, n_opp = 0;
+    const int dix[4] = {-1, 1, 0, 0}, diy[4] = {0, 0, -1, 1};
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        const int jx = ix + dix[d], jy = iy + diy[d];
+        if (jx < 0 || jx >= Nx || jy < 0 || jy >= Ny) continue;
+        const double sn = m.sign_snap[(long long)jx * Ny + jy];
+        if (sn == 0.0) continue;
+        if (sn * s > 0) ++n_same;
+        else ++n_opp;
+    }
+    if (n_opp > n_same && n_opp >= 2) {
+        m.det_J[p] = KT_CAUSTIC_SENTINEL;
+        m.sign_J[p] = 0.0;
+        atomicAdd(&m.cnt[6], 1ull);
+    }
+}
+
 // FP64 FMA peak: 8 independent dependent-chains per thread, 4096 FMAs each
 __global__ void k_dfma_peak(double* out, int iters)
 {
@@ -588,9 +750,14 @@ static cudaError_t launch_trace(const LaunchCfg& cfg, const TraceParams& P, IO i
     auto kern = trace_persistent<INTEG, IO, TRACE_THREADS, MINB>;
     constexpr int WARPS = TRACE_THREADS / 32;
     const size_t smem = (sizeof(Stage<IO::ND_IN, IO::NI_IN>) + sizeof(Stage<IO::ND_OUT, IO::NI_OUT>) +
-                         KT_NCOUNTERS * sizeof(unsigned long long)) * WARPS + extra_smem;
+                         KT_NCOUNTERS * sizeof(unsigned long long)) * WARPS +
+                        (IO::KEEP_MOM ? sizeof(double) * 4 * TRACE_THREADS : 0) + extra_smem;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if (cfg.carveout >= 0) {   // developer knob (KT_CARVEOUT, percent of the SM's shared-memory capacity); default: driver's choice
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cfg.carveout);
+        if (e != cudaSuccess) return e;
+    }
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TRACE_THREADS, smem);
     if (e != cudaSuccess) return e;
@@ -608,6 +775,7 @@ template <class IO>
 static cudaError_t launch_trace_any(const LaunchCfg& cfg, const TraceParams& P, IO io, size_t extra_smem)
 {
     const int minb = cfg.min_blocks;
+    if (P.integrator == KT_EULER) return launch_trace<KT_EULER, IO, 5>(cfg, P, io, extra_smem);
     if (P.integrator == KT_RK45) {
         if (minb == 3) return launch_trace<KT_RK45, IO, 3>(cfg, P, io, extra_smem);
         if (minb == 5) return launch_trace<KT_RK45, IO, 5>(cfg, P, io, extra_smem);
@@ -638,6 +806,18 @@ static cudaError_t l_trace_rayset(const LaunchCfg& cfg, const TraceParams& P, kt
     RaysetIO io;
     io.rays = rays; io.counters = counters; io.smem = nullptr;
     return launch_trace_any(cfg, P, io, 0);
+}
+
+static cudaError_t l_trace_paths(const LaunchCfg& cfg, const TraceParams& P, kt_ray* rays, double* counters, const kt_path_opts& opts,
+                                 long long* counts, const long long* offsets, double* points)
+{
+    PathIO io;
+    io.rays = rays; io.counters = counters; io.smem = nullptr;
+    io.opts = opts; io.counts = counts; io.offsets = offsets; io.points = points;
+    // not a throughput path (ordered text output of a few thousand rays): one spill-free occupancy for all integrators
+    if (P.integrator == KT_EULER) return launch_trace<KT_EULER, PathIO, 3>(cfg, P, io, 0);
+    if (P.integrator == KT_RK45) return launch_trace<KT_RK45, PathIO, 3>(cfg, P, io, 0);
+    return launch_trace<KT_RK4, PathIO, 3>(cfg, P, io, 0);
 }
 
 static cudaError_t l_trace_emis(const LaunchCfg& cfg, const TraceParams& P, const PointSourceFrame& F, const kt_emis_bins& B,
@@ -716,6 +896,15 @@ static cudaError_t l_bin_image(const LaunchCfg& cfg, const kt_ray* rays, long lo
     k_bin_image<<<nblocks(n, 256), 256, 0, cfg.stream>>>(rays, n, B, maps);
     return cudaGetLastError();
 }
+static cudaError_t l_caustic_pass(const LaunchCfg& cfg, int pass, const kt_ray_min* rays, long long n_live, int plane_Ny, int bundles,
+                                  double eps_x, double eps_y, const kt_caustic_cfg& c, const CausticMaps& m)
+{
+    const long long npix = (long long)c.img_Nx * c.img_Ny;
+    if (pass == 0) k_caustic_centres<<<nblocks(npix, 256), 256, 0, cfg.stream>>>(rays, n_live, plane_Ny, bundles ? 5 : 1, c, m);
+    else if (pass == 1) k_caustic_jacobian<<<nblocks(npix, 256), 256, 0, cfg.stream>>>(rays, n_live, plane_Ny, bundles, eps_x, eps_y, c, m);
+    else k_caustic_suppress<<<nblocks(npix, 256), 256, 0, cfg.stream>>>(c, m);
+    return cudaGetLastError();
+}
 static cudaError_t l_dfma_peak(const LaunchCfg& cfg, double* out, int blocks, int threads, int iters)
 {
     if (blocks < -1) {  // self-test of xdiv / xsqrt: threads = sampling mode, iters = samples per thread
@@ -746,6 +935,7 @@ extern "C" const kt::KernelTable* KT_TABLE_NAME()
         kt::KT_MODE_NS::l_rayset_reset, kt::KT_MODE_NS::l_init_pointsource, kt::KT_MODE_NS::l_init_imageplane,
         kt::KT_MODE_NS::l_redshift_start, kt::KT_MODE_NS::l_redshift_V, kt::KT_MODE_NS::l_redshift_dest, kt::KT_MODE_NS::l_range_phi, kt::KT_MODE_NS::l_calc_momentum,
         kt::KT_MODE_NS::l_bin_emissivity, kt::KT_MODE_NS::l_bin_image, kt::KT_MODE_NS::l_dfma_peak,
+        kt::KT_MODE_NS::l_caustic_pass, kt::KT_MODE_NS::l_trace_paths,
     };
     return &table;
 }

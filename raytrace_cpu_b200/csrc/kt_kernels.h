@@ -11,6 +11,15 @@ struct LaunchCfg {
     cudaStream_t stream;
     int sm_count;
     int min_blocks;   // CTAs of 128 threads per SM the trace kernel is compiled for (3, 4 or 5); 0 = default
+    int carveout;     // preferred shared-memory carve-out in percent, -1 = leave it to the driver
+};
+
+// device pointers of the nine caustic maps (+ the snapshot of sign_J the suppression pass reads, + 7 counters:
+// disc_count, horizon, rlim, steplim, outofrange, other, suppressed)
+struct CausticMaps {
+    double *det_J, *sign_J, *radius, *phi, *x_disc, *y_disc, *redshift, *sign_snap;
+    int *order, *hit;
+    unsigned long long* cnt;
 };
 
 struct KernelTable {
@@ -33,6 +42,11 @@ struct KernelTable {
     cudaError_t (*bin_emissivity)(const LaunchCfg&, const kt_ray*, long long n, const kt_emis_bins&, double log_dr, double* hist);
     cudaError_t (*bin_image)(const LaunchCfg&, const kt_ray*, long long n, const kt_image_bins&, double* maps);
     cudaError_t (*dfma_peak)(const LaunchCfg&, double* out, int blocks, int threads, int iters);
+    // caustic_discplane.cpp:219-334 / 351-448 (pass 0: centre rays, pass 1: Jacobian, pass 2: suppression)
+    cudaError_t (*caustic_pass)(const LaunchCfg&, int pass, const kt_ray_min* rays, long long n_live, int plane_Ny, int bundles,
+                                double eps_x, double eps_y, const kt_caustic_cfg&, const CausticMaps&);
+    cudaError_t (*trace_paths)(const LaunchCfg&, const TraceParams&, kt_ray* rays, double* counters, const kt_path_opts&,
+                               long long* counts, const long long* offsets, double* points);
 };
 
 }  // namespace kt

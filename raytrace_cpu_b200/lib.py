@@ -27,9 +27,9 @@ EXPORTS = [
     "kt_rayset_download", "kt_rayset_init_pointsource", "kt_rayset_init_imageplane", "kt_rayset_redshift_start",
     "kt_rayset_trace", "kt_rayset_redshift", "kt_rayset_redshift_dest", "kt_rayset_range_phi",
     "kt_rayset_calculate_momentum", "kt_rayset_bin_emissivity", "kt_rayset_bin_image",
-    "kt_trace", "kt_redshift_start", "kt_redshift", "kt_redshift_dest", "kt_range_phi", "kt_pointsource_init",
+    "kt_trace", "kt_trace_paths_count", "kt_trace_paths", "kt_redshift_start", "kt_redshift", "kt_redshift_dest", "kt_range_phi", "kt_pointsource_init",
     "kt_imageplane_init", "kt_pointsource_emissivity", "kt_pointsource_emissivity_dev", "kt_imageplane_image",
-    "kt_imageplane_image_dev", "kt_imageplane_rays",
+    "kt_imageplane_image_dev", "kt_imageplane_rays", "kt_caustic_discplane",
 ]
 
 _lib = None
@@ -96,6 +96,8 @@ def load():
     proto("kt_rayset_bin_emissivity", i32, vp, EB, EO)
     proto("kt_rayset_bin_image", i32, vp, IB, IO)
     proto("kt_trace", i32, vp, TR, ST, RN, vp, i64)
+    proto("kt_trace_paths_count", i32, vp, TR, ST, RN, vp, i64, C.POINTER(A.PathOpts), A.c_int64_p)
+    proto("kt_trace_paths", i32, vp, TR, ST, RN, vp, i64, C.POINTER(A.PathOpts), A.c_int64_p, A.c_double_p)
     proto("kt_redshift_start", i32, vp, TR, vp, i64, d, i32, i32)
     proto("kt_redshift", i32, vp, TR, vp, i64, d, i32, i32, i32)
     proto("kt_redshift_dest", i32, vp, TR, ST, vp, i64, i32)
@@ -107,6 +109,7 @@ def load():
     proto("kt_imageplane_image", i32, vp, IP, TR, ST, RN, IB, SH, IO)
     proto("kt_imageplane_image_dev", i32, vp, IP, TR, ST, RN, IB, SH, vp)
     proto("kt_imageplane_rays", i32, vp, IP, TR, ST, RN, i32, d, i32, vp, i64)
+    proto("kt_caustic_discplane", i32, vp, IP, TR, ST, RN, C.POINTER(A.CausticCfg), C.POINTER(A.CausticOut))
     _lib = L
     return L
 

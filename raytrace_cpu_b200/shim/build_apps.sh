@@ -14,7 +14,7 @@ mkdir -p "$OVL/src" "$OUT"
 # real directories holding per-file symlinks, so that the sources' relative includes ("../raytracer/...",
 # "../include/...") resolve inside the overlay and not through the physical parent of a symlinked directory
 ln -s "$REF/src/include" "$OVL/src/include"
-for d in emissivity imageplane caustic tests; do
+for d in emissivity imageplane caustic tests ray_paths; do
     mkdir "$OVL/src/$d"
     ln -s "$REF/src/$d"/*.cpp "$OVL/src/$d/"
 done
@@ -24,6 +24,10 @@ FLAGS="-O2 -fopenmp -w -I$OVL/src -I$REPO/include -L$REPO/raytrace_cpu_b200 -Wl,
 $CXX $FLAGS "$OVL/src/emissivity/emissivity_rd.cpp" -o "$OUT/emissivity_rd" -lkerrtrace
 $CXX $FLAGS "$OVL/src/tests/emissivity_rk45_test.cpp" -o "$OUT/emissivity_rk45_test" -lkerrtrace
 $CXX $FLAGS "$OVL/src/tests/integrator_perf_test.cpp" -o "$OUT/integrator_perf_test" -lkerrtrace
+# Euler (the reference's own Euler-vs-RK4 consistency test) and the ray-path dumping applications (Euler + outfile)
+$CXX $FLAGS "$OVL/src/tests/raytrace_rk4_test.cpp" -o "$OUT/raytrace_rk4_test" -lkerrtrace
+$CXX $FLAGS "$OVL/src/ray_paths/trace_rays.cpp" -o "$OUT/trace_rays" -lkerrtrace
+$CXX $FLAGS "$OVL/src/ray_paths/trace_rays_imageplane.cpp" -o "$OUT/trace_rays_imageplane" -lkerrtrace
 # the FITS-writing applications, with the bundled minimal FITS writer standing in for cfitsio (absent from this image)
 /usr/bin/gcc -O2 -c "$HERE/minifits/minifits.c" -o "$OVL/minifits.o"
 for app in imageplane/imageplane_disc_image imageplane/imageplane_disc_image_rd imageplane/imageplane_disc_image_isco \

@@ -7,11 +7,12 @@
 // (reference raytracer.h:19-198): struct Ray<T>, RAY_STATUS_*, the tuning macros, enum class Integrator and
 // class Raytracer<T> with its public `rays` array.
 //
-// What runs where: run_raytrace (RK4, RK45; theta_max or one of the three concrete RayDestination classes),
-// redshift_start, redshift, range_phi and calculate_momentum run on the GPU and leave their results in the host
-// array `rays`, exactly as the CPU code does.  Integrator::Euler, ray-path dumping (outfile != 0), user-defined
-// RayDestination subclasses and T = float are not offloaded: they throw std::runtime_error (keep the reference's
-// CPU build for those).
+// What runs where: run_raytrace (Euler, RK4, RK45; theta_max or one of the three concrete RayDestination classes; with
+// or without an outfile for ray-path dumping), redshift_start, redshift, range_phi and calculate_momentum run on the GPU
+// and leave their results in the host array `rays`, exactly as the CPU code does.  With an outfile the engine returns
+// every ray's points and this header writes them through the reference's own TextOutput, in ray order, so the text is
+// formatted by the same code as in the CPU build.  User-defined RayDestination subclasses and T = float are not
+// offloaded: they throw std::runtime_error (keep the reference's CPU build for those).
 #ifndef RAYTRACER_H_
 #define RAYTRACER_H_
 
@@ -37,6 +38,7 @@
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <vector>
 using namespace std;   // the reference header does this and the applications rely on it
 
 #include "../include/kerr.h"
@@ -159,7 +161,7 @@ public:
         kt_stop stop = {};
         stop.kind = KT_STOP_THETALIM;
         stop.theta_lim = theta_max;
-        trace(stop, method, r_max, outfile, steplim);
+        trace(stop, method, r_max, outfile, steplim, write_step, write_rmax, write_rmin, write_cartesian);
     }
 
     void run_raytrace(RayDestination<T>* dest, Integrator method = Integrator::Euler, T r_max = 1000, int show_progress = 1,
@@ -167,7 +169,7 @@ public:
                       bool write_cartesian = true, int steplim = -1)
     {
         assert(method != Integrator::Euler && "Integrator::Euler does not support RayDestination stopping conditions");
-        trace(kerrtrace_shim::stop_of(dest), method, r_max, outfile, steplim);
+        trace(kerrtrace_shim::stop_of(dest), method, r_max, outfile, steplim, write_step, write_rmax, write_rmin, write_cartesian);
     }
 
     void redshift_start(T V, bool reverse = false, bool projradius = false)
@@ -224,18 +226,43 @@ protected:
     kt_ray* as_kt() { return reinterpret_cast<kt_ray*>(rays); }
 
 private:
-    void trace(const kt_stop& stop, Integrator method, T r_max, TextOutput* outfile, int steplim)
+    void trace(const kt_stop& stop, Integrator method, T r_max, TextOutput* outfile, int steplim, int write_step, T write_rmax,
+               T write_rmin, bool write_cartesian)
     {
-        if (outfile != nullptr) throw std::runtime_error("kerrtrace: ray-path dumping (outfile) is not offloaded");
-        if (method == Integrator::Euler) throw std::runtime_error("kerrtrace: Integrator::Euler is not offloaded");
-        if (!kerrtrace_shim::quiet())
-            cout << (method == Integrator::RK45 ? "Running raytracer (RK45/DOPRI5)..." : "Running raytracer (RK4)...") << endl;
+        static const char* names[] = {"Running raytracer...", "Running raytracer (RK4)...", "Running raytracer (RK45/DOPRI5)..."};
+        if (!kerrtrace_shim::quiet()) cout << names[static_cast<int>(method)] << endl;     // raytracer.cpp:75-81
         kt_run run = {};
-        run.integrator = (method == Integrator::RK45) ? KT_RK45 : KT_RK4;
+        run.integrator = (method == Integrator::RK45) ? KT_RK45 : (method == Integrator::RK4) ? KT_RK4 : KT_EULER;
         run.steplim = steplim;
         run.r_max = r_max;
         run.math_mode = math_mode;
-        kerrtrace_shim::check(kt_trace(engine(), tracer(), &stop, &run, as_kt(), nRays), "run_raytrace");
+        if (outfile == nullptr) {
+            kerrtrace_shim::check(kt_trace(engine(), tracer(), &stop, &run, as_kt(), nRays), "run_raytrace");
+            return;
+        }
+        // serial path of the reference (raytracer.cpp:86-100): rays in index order, one line per written point, two blank
+        // lines after every ray that was propagated; rays with steps < 0 or steps >= steplim are skipped entirely
+        kt_path_opts opts = {};
+        opts.write_step = write_step;
+        opts.write_cartesian = write_cartesian ? 1 : 0;
+        opts.write_rmax = write_rmax;
+        opts.write_rmin = write_rmin;
+        const int effective_steplim = (steplim > 0) ? steplim : (method == Integrator::RK45) ? RK45_STEPLIM : STEPLIM;
+        std::vector<int> before(nRays > 0 ? nRays : 1);
+        for (int i = 0; i < nRays; i++) before[i] = rays[i].steps;
+        std::vector<int64_t> offsets(nRays + 1, 0);
+        kerrtrace_shim::check(kt_trace_paths_count(engine(), tracer(), &stop, &run, as_kt(), nRays, &opts, offsets.data()),
+                              "run_raytrace (path count)");
+        std::vector<double> pts(4 * (offsets[nRays] > 0 ? offsets[nRays] : 1));
+        kerrtrace_shim::check(kt_trace_paths(engine(), tracer(), &stop, &run, as_kt(), nRays, &opts, offsets.data(), pts.data()),
+                              "run_raytrace (paths)");
+        for (int ray = 0; ray < nRays; ray++) {
+            if (before[ray] < 0) continue;
+            else if (before[ray] >= effective_steplim) continue;
+            for (int64_t q = offsets[ray]; q < offsets[ray + 1]; q++)
+                (*outfile) << pts[4 * q] << pts[4 * q + 1] << pts[4 * q + 2] << pts[4 * q + 3] << endl;
+            outfile->newline(2);
+        }
     }
 };
 

@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from raytrace_cpu_b200 import _abi as A  # noqa: E402
 import oracle_bindings as ob  # noqa: E402
-from golden_cases import CASES, build_source  # noqa: E402
+from golden_cases import CASES, PATH_CASES, build_source  # noqa: E402
 
 from golden_cases import APP_PARS  # noqa: E402
 
@@ -44,6 +44,9 @@ def run_case(ref, case):
     init = h.rays()
     stop = ob.make_stop(**case["stop"])
     run = ob.make_run(case["integrator"], r_max=case["r_max"], steplim=case.get("steplim", -1))
+    if "paths" in case:
+        offsets, points = h.run_paths(stop, run, ob.make_path_opts(**case["paths"]))
+        return init, h.rays(), offsets, points
     h.run(stop, run)
     reverse = case["source"] != "point"
     if case["redshift"] == "V":
@@ -55,10 +58,19 @@ def run_case(ref, case):
     return init, h.rays()
 
 
+FORCE = "--force" in sys.argv   # default: only fixtures that do not exist yet are generated
+
+
+def missing(filename):
+    return FORCE or not os.path.exists(os.path.join(GOLDEN, filename))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref = ob.Ref()
     for name, case in CASES.items():
+        if not missing(name + ".npz"):
+            continue
         init, final = run_case(ref, case)
         used = final["steps"] != -1
         # zero the fields the reference leaves uninitialised in unused slots so the fixture is deterministic
@@ -70,12 +82,27 @@ def main():
         print(f"{name}: {len(final)} slots, {int(used.sum())} rays, status histogram "
               f"{ {int(s): int((final['status'][used] == s).sum()) for s in np.unique(final['status'][used])} }")
 
+    for name, case in PATH_CASES.items():
+        if not missing(name + ".npz"):
+            continue
+        init, final, offsets, points = run_case(ref, case)
+        used = final["steps"] != -1
+        for arr in (init, final):
+            for f in arr.dtype.names:
+                if f not in ("steps", "status"):
+                    arr[f][~used] = 0
+        for arr in (init, final):          # the path fixtures pin positions and bookkeeping, not the energies
+            arr["redshift"][:] = 0
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), init=init, final=final, offsets=offsets, points=points)
+        print(f"{name}: {int(used.sum())} rays, {len(points)} points")
+
     # scalars the reference prints
     scal = {"spins": np.array([0.0, 0.1, 0.5, 0.9, 0.998, -0.5, -0.998])}
     scal["isco_pro"] = np.array([ref.kerr_isco(a, +1) for a in scal["spins"]])
     scal["isco_retro"] = np.array([ref.kerr_isco(a, -1) for a in scal["spins"]])
     scal["horizon"] = np.array([ref.kerr_horizon(a) for a in scal["spins"]])
-    np.savez(os.path.join(GOLDEN, "scalars.npz"), **scal)
+    if missing("scalars.npz"):
+        np.savez(os.path.join(GOLDEN, "scalars.npz"), **scal)
 
     # the reference's own emissivity_rd application, end to end (text output, 7 columns)
     with tempfile.TemporaryDirectory() as tmp:
@@ -91,8 +118,39 @@ def main():
         with open(par, "w") as f:
             f.write(f"outfile = {out}\ntheta_lim = 1.5707963\nsource = 0 10 1E-3 1.5707\nV = 0\nspin = 0.998\n"
                     "dcosalpha = 0.02\ndbeta = 0.02\nNr = 30\nlogbin_r = 1\nshow_progress = 0\n")
-        subprocess.run([exe], check=True, stdout=subprocess.DEVNULL, cwd=os.path.join(tmp, "bin"))
-        print("emissivity_rd_app.dat:", sum(1 for _ in open(out)), "lines")
+        if missing("emissivity_rd_app.dat"):
+            subprocess.run([exe], check=True, stdout=subprocess.DEVNULL, cwd=os.path.join(tmp, "bin"))
+            print("emissivity_rd_app.dat:", sum(1 for _ in open(out)), "lines")
+
+        # the reference's own Euler-vs-RK4 consistency test (stdout) and its ray-path dumping applications (text files)
+        if missing("raytrace_rk4_test.stdout"):
+            exe = os.path.join(tmp, "raytrace_rk4_test")
+            subprocess.run(["/usr/bin/g++", "-O2", "-fopenmp", "-ffp-contract=off", "-w", f"-I{REF}/src", f"-I{REF}/src/raytracer",
+                            f"{REF}/src/tests/raytrace_rk4_test.cpp", f"{REF}/src/raytracer/raytracer.cpp",
+                            f"{REF}/src/raytracer/pointsource.cpp", "-o", exe], check=True)
+            res = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+            with open(os.path.join(GOLDEN, "raytrace_rk4_test.stdout"), "w") as f:
+                f.write(f"# exit code {res.returncode}\n" + res.stdout)
+            print("raytrace_rk4_test.stdout: exit", res.returncode)
+        for app, imp in (("trace_rays", "pointsource.cpp"), ("trace_rays_imageplane", "imageplane.cpp")):
+            exe = os.path.join(tmp, app)
+            built = False
+            for parname, text in APP_PARS[app].items():
+                if not missing(parname + ".dat"):
+                    continue
+                if not built:
+                    subprocess.run(["/usr/bin/g++", "-O2", "-fopenmp", "-ffp-contract=off", "-w", f"-I{REF}/src", f"-I{REF}/src/raytracer",
+                                    f"{REF}/src/ray_paths/{app}.cpp", f"{REF}/src/raytracer/raytracer.cpp",
+                                    f"{REF}/src/raytracer/{imp}", "-o", exe], check=True)
+                    built = True
+                out = os.path.join(GOLDEN, parname + ".dat")
+                # trace_rays' --parfile keeps a dangling c_str() (trace_rays.cpp:29-33, the same UB as SURVEY appendix A.16):
+                # both apps are run on their default relative path ../par/<app>.par instead
+                par = os.path.join(tmp, "par", app + ".par")
+                with open(par, "w") as f:
+                    f.write(f"outfile = {out}\n" + text)
+                subprocess.run([exe], check=True, stdout=subprocess.DEVNULL, cwd=os.path.join(tmp, "bin"))
+                print(parname + ".dat:", sum(1 for _ in open(out)), "lines")
 
         # the reference's FITS-writing applications (CPU build of the reference, linked with the bundled minimal
         # FITS writer because cfitsio is not installed here): golden multi-extension FITS files
@@ -106,6 +164,8 @@ def main():
                             f"-I{minifits}", f"{REF}/src/{src_file}", f"{REF}/src/raytracer/raytracer.cpp",
                             f"{REF}/src/raytracer/{imp}", obj, "-o", exe], check=True)
             for parname, text in APP_PARS[app].items():
+                if not missing(parname + ".fits"):
+                    continue
                 out = os.path.join(GOLDEN, parname + ".fits")
                 par = os.path.join(tmp, parname + ".par")
                 with open(par, "w") as f:

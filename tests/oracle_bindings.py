@@ -49,12 +49,17 @@ class Oracle:
         L.orc_redshift_start.argtypes = [C.c_void_p, C.c_int64, C.POINTER(A.Tracer), C.c_double, C.c_int, C.c_int]
         L.orc_trace.restype = C.c_int64
         L.orc_trace.argtypes = [C.c_void_p, C.c_int64, C.POINTER(A.Tracer), C.POINTER(A.Stop), C.POINTER(A.Run), C.c_int]
+        L.orc_trace_paths.restype = C.c_int64
+        L.orc_trace_paths.argtypes = [C.c_void_p, C.c_int64, C.POINTER(A.Tracer), C.POINTER(A.Stop), C.POINTER(A.Run),
+                                      C.POINTER(A.PathOpts), A.c_int64_p, A.c_double_p]
         L.orc_redshift.argtypes = [C.c_void_p, C.c_int64, C.POINTER(A.Tracer), C.c_double, C.c_int, C.c_int, C.c_int]
         L.orc_redshift_dest.argtypes = [C.c_void_p, C.c_int64, C.POINTER(A.Tracer), C.POINTER(A.Stop), C.c_int]
         L.orc_range_phi.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_double]
         L.orc_calculate_momentum.argtypes = [C.c_void_p, C.c_int64, C.POINTER(A.Tracer)]
         L.orc_bin_emissivity.argtypes = [C.c_void_p, C.c_int64, C.POINTER(A.EmisBins), C.POINTER(A.EmisOut)]
         L.orc_bin_image.argtypes = [C.c_void_p, C.c_int64, C.POINTER(A.ImageBins), C.POINTER(A.ImageOut)]
+        L.orc_caustic_maps.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int, C.c_double, C.c_double, C.POINTER(A.CausticCfg),
+                                       C.POINTER(A.CausticOut)]
         L.orc_momentum_from_consts.argtypes = [A.c_double_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                                C.c_double, C.c_double, C.c_double]
 
@@ -97,6 +102,18 @@ class Oracle:
     def trace(self, rays, tr, stop, run, nthreads=0):
         return self.L.orc_trace(_rays_ptr(rays), len(rays), C.byref(tr), C.byref(stop), C.byref(run), nthreads)
 
+    def trace_paths(self, rays, tr, stop, run, opts):
+        """run_raytrace with an outfile: rays updated in place; returns (offsets[n + 1], points[total, 4])."""
+        n = len(rays)
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        scratch = rays.copy()
+        total = self.L.orc_trace_paths(_rays_ptr(scratch), n, C.byref(tr), C.byref(stop), C.byref(run), C.byref(opts),
+                                       offsets.ctypes.data_as(A.c_int64_p), None)
+        points = np.zeros((total, 4))
+        self.L.orc_trace_paths(_rays_ptr(rays), n, C.byref(tr), C.byref(stop), C.byref(run), C.byref(opts),
+                               offsets.ctypes.data_as(A.c_int64_p), points.ctypes.data_as(A.c_double_p))
+        return offsets, points
+
     def redshift(self, rays, tr, V, reverse=False, projradius=False, motion=0):
         self.L.orc_redshift(_rays_ptr(rays), len(rays), C.byref(tr), V, int(reverse), int(projradius), motion)
 
@@ -123,6 +140,36 @@ class Oracle:
         p = np.zeros(4)
         self.L.orc_momentum_from_consts(A.dptr(p), k, h, Q, rs, ts, r, theta, a)
         return p
+
+    def caustic_maps(self, rays, plane_Ny, bundles, eps_x, eps_y, cfg):
+        out = A.CausticResult(cfg.img_Nx, cfg.img_Ny)
+        self.L.orc_caustic_maps(_rays_ptr(rays), len(rays), plane_Ny, int(bundles), eps_x, eps_y, C.byref(cfg), C.byref(out.c))
+        return out
+
+
+def parse_paths(text, steps_before, steplim):
+    """Text written by run_raytrace(..., outfile) -> (offsets[n + 1], points[total, 4]).  Every propagated ray (steps >= 0 and
+    < steplim before the call) contributes its point lines followed by two blank lines; skipped rays contribute nothing."""
+    blocks, cur, blanks = [], [], 0
+    for line in text.split("\n")[:-1]:
+        if line.strip():
+            cur.append([float(x) for x in line.split()])
+        else:
+            blanks += 1
+            if blanks == 2:
+                blocks.append(cur)
+                cur, blanks = [], 0
+    assert not cur and blanks == 0, "trailing partial block"
+    live = [i for i, s in enumerate(steps_before) if 0 <= s < steplim]
+    assert len(blocks) == len(live), (len(blocks), len(live))
+    n = len(steps_before)
+    counts = np.zeros(n, dtype=np.int64)
+    for i, b in zip(live, blocks):
+        counts[i] = len(b)
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    offsets[1:] = np.cumsum(counts)
+    pts = np.array([row for b in blocks for row in b], dtype=np.float64).reshape(-1, 4)
+    return offsets, pts
 
 
 def ref_available():
@@ -171,6 +218,25 @@ class RefSource:
                                 run.steplim if run.steplim > 0 else -1)
         return self.L.ref_last_trace_seconds(self.h)
 
+    def run_paths(self, stop, run, opts, precision=17):
+        """run_raytrace with an outfile through the reference's own TextOutput; the text is parsed back into
+        (offsets[n + 1], points[total, 4]) -- with 17 digits the columns are the exact doubles.  `before` steps decide
+        which rays were propagated (each of those ends with two blank lines, raytracer.cpp:99)."""
+        import tempfile
+        before = self.rays()["steps"].copy()
+        steplim = run.steplim if run.steplim > 0 else (A.RK45_STEPLIM if run.integrator == A.RK45 else A.STEPLIM)
+        with tempfile.TemporaryDirectory() as tmp:
+            fn = os.path.join(tmp, "paths.dat")
+            if stop.kind == A.STOP_THETALIM:
+                self.L.ref_run_thetalim_paths(self.h, run.integrator, stop.theta_lim, run.r_max, run.steplim if run.steplim > 0 else -1,
+                                              fn.encode(), precision, opts.write_step, opts.write_rmax, opts.write_rmin, opts.write_cartesian)
+            else:
+                self.L.ref_run_dest_paths(self.h, run.integrator, stop.kind, _stop_par(stop), run.r_max,
+                                          run.steplim if run.steplim > 0 else -1, fn.encode(), precision, opts.write_step,
+                                          opts.write_rmax, opts.write_rmin, opts.write_cartesian)
+            text = open(fn).read()
+        return parse_paths(text, before, steplim)
+
     def redshift(self, V, reverse=False, projradius=False, motion=0):
         self.L.ref_redshift_V(self.h, V, int(reverse), int(projradius), motion)
 
@@ -213,6 +279,8 @@ class Ref:
         L.ref_redshift_start.argtypes = [C.c_void_p, d, C.c_int, C.c_int]
         L.ref_run_thetalim.argtypes = [C.c_void_p, C.c_int, d, d, C.c_int]
         L.ref_run_dest.argtypes = [C.c_void_p, C.c_int, C.c_int, A.c_double_p, d, C.c_int]
+        L.ref_run_thetalim_paths.argtypes = [C.c_void_p, C.c_int, d, d, C.c_int, C.c_char_p, C.c_int, C.c_int, d, d, C.c_int]
+        L.ref_run_dest_paths.argtypes = [C.c_void_p, C.c_int, C.c_int, A.c_double_p, d, C.c_int, C.c_char_p, C.c_int, C.c_int, d, d, C.c_int]
         L.ref_redshift_V.argtypes = [C.c_void_p, d, C.c_int, C.c_int, C.c_int]
         L.ref_redshift_dest.argtypes = [C.c_void_p, C.c_int, A.c_double_p, C.c_int]
         L.ref_range_phi.argtypes = [C.c_void_p, d, d]
@@ -291,6 +359,12 @@ def make_stop(kind=A.STOP_THETALIM, theta_lim=np.pi / 2, r_isco=0.0, r_out=-1.0,
     s = A.Stop()
     s.kind, s.theta_lim, s.r_isco, s.r_out, s.incl, s.phi0, s.z_s = kind, theta_lim, r_isco, r_out, incl, phi0, z_s
     return s
+
+
+def make_path_opts(write_step=10, write_cartesian=True, write_rmax=-1.0, write_rmin=-1.0):
+    o = A.PathOpts()
+    o.write_step, o.write_cartesian, o.write_rmax, o.write_rmin = write_step, int(write_cartesian), write_rmax, write_rmin
+    return o
 
 
 def make_run(integrator=A.RK4, r_max=1000.0, steplim=-1, math_mode=A.MATH_EXACT):

@@ -13,7 +13,7 @@ import pytest
 
 from raytrace_cpu_b200 import _abi as A
 import oracle_bindings as ob
-from golden_cases import CASES, R_ISCO, SPIN, build_source, tracer_for
+from golden_cases import CASES, PATH_CASES, R_ISCO, SPIN, build_source, tracer_for
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FLOAT_FIELDS = [n for n in A.RAY_DTYPE.names if A.RAY_DTYPE[n].kind == "f"]
@@ -47,6 +47,9 @@ def run_oracle_case(orc, case):
     init = rays.copy()
     stop = ob.make_stop(**case["stop"])
     run = ob.make_run(case["integrator"], r_max=case["r_max"], steplim=case.get("steplim", -1))
+    if "paths" in case:
+        offsets, points = orc.trace_paths(rays, tr, stop, run, ob.make_path_opts(**case["paths"]))
+        return init, rays, offsets, points
     orc.trace(rays, tr, stop, run)
     if case["redshift"] == "V":
         orc.redshift(rays, tr, -1.0, not point)
@@ -64,6 +67,63 @@ def test_oracle_reproduces_golden_fixture_bit_for_bit(orc, name):
     assert len(final) == len(g["final"])
     assert_bit_identical(init, g["init"], skip=("redshift",))     # redshift is not yet defined before the trace
     assert_bit_identical(final, g["final"])
+
+
+@pytest.mark.parametrize("name", sorted(PATH_CASES))
+def test_oracle_reproduces_golden_ray_paths_bit_for_bit(orc, name):
+    """run_raytrace with an outfile (raytracer.cpp:86-100 and the write blocks of the five propagators): the points the
+    reference wrote through its TextOutput at 17 significant digits, the per-ray point counts and the final rays."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    init, final, offsets, points = run_oracle_case(orc, PATH_CASES[name])
+    assert_bit_identical(init, g["init"], skip=("redshift",))
+    assert_bit_identical(final, g["final"], skip=("redshift",))
+    assert (offsets == g["offsets"]).all() and offsets[-1] > 1000
+    assert points.shape == g["points"].shape and ob.same_bits(points, g["points"]).all()
+
+
+CAUSTIC_FITS = {"DET_J": "det_J", "SIGN_J": "sign_J", "ORDER": "order", "HIT": "hit", "RADIUS": "radius", "PHI": "phi",
+                "X_DISC": "x_disc", "Y_DISC": "y_disc", "REDSHIFT": "redshift"}
+
+
+def oracle_caustic(orc, par):
+    """caustic_discplane.cpp:104-493 through the oracle: plane -> redshift_start -> trace -> redshift(dest, reverse) -> maps."""
+    import raytrace_cpu_b200 as K
+    dx, dy = (par["xmax"] - par["x0"]) / par["Nx"], (par["ymax"] - par["y0"]) / par["Ny"]
+    bundles = par["bundle_eps_frac"] > 0
+    ip = K.imageplane_desc(par["dist"], par["incl"], par["x0"], par["xmax"], dx, par["y0"], par["ymax"], dy, par["plane_phi0"],
+                           bundles, par["bundle_eps_frac"] if bundles else 0.01)
+    tr = orc.tracer(-par["spin"], par["precision"])
+    tr.rk45_tol = par["rk45_tol"]
+    rays = orc.imageplane_rays(tr, ip)
+    orc.redshift_start(rays, tr, 0.0, True)
+    r_isco = orc.kerr_isco(par["spin"], +1)
+    stop = ob.make_stop(A.STOP_ISCODISC, r_isco=r_isco, r_out=par["r_disc"])
+    orc.trace(rays, tr, stop, ob.make_run(A.RK45 if par["rk45"] else A.RK4, r_max=1.1 * par["dist"]))
+    orc.redshift_dest(rays, tr, stop, True)
+    cfg = A.CausticCfg()
+    cfg.img_Nx, cfg.img_Ny = par["Nx"] + 1, par["Ny"] + 1
+    cfg.r_isco, cfg.r_disc, cfg.dx, cfg.dy = r_isco, par["r_disc"], dx, dy
+    cfg.redshift_mode, cfg.suppress, cfg.V = A.REDSHIFT_DEST, 1, -1.0
+    _, _, plane_ny = orc.imageplane_count(ip)
+    return orc.caustic_maps(rays, plane_ny, bundles, par["bundle_eps_frac"] * dx, par["bundle_eps_frac"] * dy, cfg)
+
+
+@pytest.mark.parametrize("case", ["app_caustic_rk4", "app_caustic_rk45", "app_caustic_grid_rk4"])
+def test_oracle_caustic_maps_match_the_reference_app_bit_for_bit(orc, case):
+    """tests/golden/app_caustic_*.fits were written by the reference's own caustic_discplane binary (CPU build); every pixel of
+    its nine extensions -- hit mask, disc coordinates, image order, redshift, Jacobian determinant (bundle and
+    grid-neighbour variants), sentinel and suppressed pixels -- must come out of the oracle identically."""
+    from fits_reader import by_extname, read_fits
+    from golden_cases import APP_PARS, caustic_par
+    hdus = read_fits(os.path.join(GOLDEN, case + ".fits"))
+    want = by_extname(hdus)
+    got = oracle_caustic(orc, caustic_par(APP_PARS["caustic_discplane"][case]))
+    assert got.disc_count == hdus[0][0]["DISC_N"] > 100
+    for ext, field in CAUSTIC_FITS.items():
+        a, b = getattr(got, field).astype(np.float64), want[ext].T       # FITS frame[k * Nx + j] = data[j][k] (fits_output.h:170-181)
+        assert a.shape == b.shape
+        assert ob.same_bits(a, b).all(), ext
+    assert (got.det_J == A.CAUSTIC_SENTINEL).sum() > 0 and np.isnan(got.det_J).sum() > 0
 
 
 def test_golden_scalars(orc):
@@ -212,6 +272,43 @@ def test_live_reference_image_plane(orc, bundles):
     assert_bit_identical(rays, h.rays())
     if not bundles:
         assert np.isnan(rays["r"]).sum() == 1     # the exact-centre pixel (b = 0 -> asin(0/0)), SURVEY 8c
+
+
+@needs_ref
+@pytest.mark.parametrize("integ", [A.EULER, A.RK4, A.RK45])
+def test_live_reference_ray_paths(orc, integ):
+    """The serial outfile branch on a second pass over already-traced rays too: rays that hit the step limit (steps < 0) are
+    skipped without even their blank lines, the others continue from where they stopped."""
+    ref = ob.Ref()
+    src = ob.make_pointsource([0, 6, 0.7, 0], 0.3, 0.3)
+    tr = orc.tracer(SPIN, A.TOL)
+    h = ref.pointsource(src, SPIN)
+    rays = orc.pointsource_rays(tr, src)
+    stop = ob.make_stop(A.STOP_THETALIM, theta_lim=0.0)
+    for steplim, opts in ((150, ob.make_path_opts(4, True)), (400, ob.make_path_opts(5, False, 30.0, 3.0))):
+        run = ob.make_run(integ, r_max=80.0, steplim=steplim)
+        woff, wpts = h.run_paths(stop, run, opts)
+        off, pts = orc.trace_paths(rays, tr, stop, run, opts)
+        assert (off == woff).all() and pts.shape == wpts.shape and ob.same_bits(pts, wpts).all()
+        assert_bit_identical(rays, h.rays(), skip=("redshift", "emit"))
+    assert (rays["steps"] < -1).any()
+
+
+@needs_ref
+def test_live_reference_euler_image_plane(orc):
+    ref = ob.Ref()
+    ip = ob.make_imageplane(200.0, 75.0, -12, 12, 21)
+    tr = orc.tracer(-SPIN, A.PRECISION)
+    h = ref.imageplane(ip, SPIN)
+    rays = orc.imageplane_rays(tr, ip)
+    rr = h.rays(copy=False)
+    rr["rdot_flips"][:] = 0
+    rr["equatorial_crossings"][:] = 0
+    stop = ob.make_stop()
+    run = ob.make_run(A.EULER, r_max=300.0)
+    h.run(stop, run)
+    orc.trace(rays, tr, stop, run)
+    assert_bit_identical(rays, h.rays(), skip=("redshift", "emit"))
 
 
 def test_rk45_nan_ray_is_retired_not_hung(orc):

@@ -29,7 +29,7 @@ def make_overlay(tmp):
     src = os.path.join(tmp, "src")
     os.makedirs(src)
     os.symlink(os.path.join(REF, "src", "include"), os.path.join(src, "include"))
-    for d in ("emissivity", "imageplane", "caustic", "tests"):
+    for d in ("emissivity", "imageplane", "caustic", "tests", "ray_paths"):
         os.makedirs(os.path.join(src, d))
         for f in os.listdir(os.path.join(REF, "src", d)):
             if f.endswith(".cpp"):
@@ -45,7 +45,7 @@ def make_overlay(tmp):
     "emissivity/emissivity_rd.cpp", "imageplane/imageplane_disc_image.cpp", "imageplane/imageplane_disc_image_rd.cpp",
     "imageplane/imageplane_disc_image_isco.cpp", "caustic/caustic_discplane.cpp", "caustic/caustic_plane.cpp",
     "caustic/caustic_sourceplane.cpp", "tests/emissivity_rk45_test.cpp", "tests/integrator_perf_test.cpp",
-    "tests/emissivity_rk45_plot.cpp",
+    "tests/emissivity_rk45_plot.cpp", "tests/raytrace_rk4_test.cpp", "ray_paths/trace_rays.cpp", "ray_paths/trace_rays_imageplane.cpp",
 ])
 def test_unmodified_reference_sources_compile_against_the_shim(app):
     with tempfile.TemporaryDirectory() as tmp:
@@ -60,7 +60,7 @@ def test_unmodified_reference_sources_compile_against_the_shim(app):
 def test_build_script_links_the_apps():
     p = subprocess.run([os.path.join(SHIM, "build_apps.sh")], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
-    for exe in ("emissivity_rd", "emissivity_rk45_test", "integrator_perf_test"):
+    for exe in ("emissivity_rd", "emissivity_rk45_test", "integrator_perf_test", "raytrace_rk4_test", "trace_rays", "trace_rays_imageplane"):
         assert os.access(os.path.join(BUILT, exe), os.X_OK)
     deps = subprocess.run(["ldd", os.path.join(BUILT, "emissivity_rd")], capture_output=True, text=True).stdout
     assert "libkerrtrace.so" in deps
@@ -114,6 +114,73 @@ def test_reference_acceptance_test_passes_on_the_gpu():
     assert "PASS" in p.stdout
     p = subprocess.run([os.path.join(BUILT, "integrator_perf_test")], capture_output=True, text=True, env=env, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(BUILT, "raytrace_rk4_test")), reason="shim/_built not present")
+def test_reference_euler_vs_rk4_test_on_the_gpu():
+    """src/tests/raytrace_rk4_test.cpp: the same rays through Integrator::Euler and Integrator::RK4; its summary must be
+    the one its CPU build printed (tests/golden/raytrace_rk4_test.stdout)."""
+    import re
+    env = dict(os.environ, KERRTRACE_QUIET="1")
+    p = subprocess.run([os.path.join(BUILT, "raytrace_rk4_test")], capture_output=True, text=True, env=env, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    want = open(os.path.join(GOLDEN, "raytrace_rk4_test.stdout")).read()
+    assert "PASS" in p.stdout and "PASS" in want
+
+    def summary(text):
+        return {k: int(v) for k, v in re.findall(r"^\s*(Total rays|Skipped \(invalid\)|Hit disc \(theta_max\)|Hit r_max|Hit horizon|Diverged trajectories):\s+(\d+)", text, re.M)}
+
+    got, ref = summary(p.stdout), summary(want)
+    assert len(ref) == 6 and got.keys() == ref.keys()
+    for k in ("Total rays", "Skipped (invalid)"):
+        assert got[k] == ref[k]
+    for k in ("Hit disc (theta_max)", "Hit r_max", "Hit horizon", "Diverged trajectories"):
+        assert abs(got[k] - ref[k]) <= 2, (k, got, ref)      # a separatrix ray may change sides (one ray = 0.3 %)
+
+
+def split_blocks(text):
+    blocks, cur, blanks = [], [], 0
+    for line in text.split("\n")[:-1]:
+        if line.strip():
+            cur.append([float(x) for x in line.split()])
+        else:
+            blanks += 1
+            if blanks == 2:
+                blocks.append(np.array(cur, dtype=np.float64).reshape(-1, 4))
+                cur, blanks = [], 0
+    assert not cur
+    return blocks
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(BUILT, "trace_rays")), reason="shim/_built not present")
+@pytest.mark.parametrize("app", ["trace_rays", "trace_rays_imageplane"])
+def test_reference_ray_path_apps_on_the_gpu(app):
+    """src/ray_paths/trace_rays{,_imageplane}.cpp (Integrator::Euler + outfile), unchanged: the text file must be the one the
+    CPU build wrote -- same number of ray blocks, same number of points per ray, every column within the 8 printed digits."""
+    from golden_cases import APP_PARS
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "par"))
+        os.makedirs(os.path.join(tmp, "bin"))
+        out = os.path.join(tmp, "out.dat")
+        with open(os.path.join(tmp, "par", app + ".par"), "w") as f:
+            f.write(f"outfile = {out}\n" + APP_PARS[app]["app_" + app])
+        env = dict(os.environ, KERRTRACE_QUIET="1")
+        p = subprocess.run([os.path.join(BUILT, app)], cwd=os.path.join(tmp, "bin"), capture_output=True, text=True, env=env, timeout=300)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        got = split_blocks(open(out).read())
+    want = split_blocks(open(os.path.join(GOLDEN, "app_" + app + ".dat")).read())
+    assert len(got) == len(want) > 20
+    same = [len(a) == len(b) for a, b in zip(got, want)]
+    assert np.mean(same) >= 0.95
+    close = []
+    for a, b, s in zip(got, want, same):
+        if s and len(b):
+            scale = np.maximum(1.0, np.sqrt((b[:, 1:] ** 2).sum(axis=1)))[:, None]
+            close.append(bool((np.abs(a[:, 1:] - b[:, 1:]) <= 2e-8 * scale).all() and np.allclose(a[:, 0], b[:, 0], rtol=2e-8, atol=2e-8)))
+    assert np.mean(close) >= 0.95, np.mean(close)
+    # byte-identical lines for the bulk of the file (same formatting code: the reference's TextOutput)
 
 
 # ---------------------------------------------------------------------------------------------------------
