@@ -257,7 +257,8 @@ int64_t kt_kernel_launches(kt_ctx*);    /* number of kernels this ctx has launch
 /* DFMA micro-benchmark: measured FP64 FMA peak in TFLOP/s (2 flop per FMA) -- the roofline denominator. */
 int kt_fp64_peak(kt_ctx*, double* tflops);
 /* bit-exactness self-test of the engine's IEEE division / square root (see csrc/kt_device.cuh: xdiv, xsqrt):
- * counts[5] = {wrong quotients, wrong roots, quotients sent to the slow path, roots sent to the slow path, samples} */
+ * counts[5] = {wrong quotients, wrong roots, quotients sent to the slow path, roots sent to the slow path, samples};
+ * mode 3 tests the exact mode's sincos against the CUDA library's: counts = {wrong sines, wrong cosines, 0, 0, samples} */
 int kt_selftest_divsqrt(kt_ctx*, int mode, int samples_per_thread, int64_t* counts);
 /* dependent-issue latency of one DFMA in SM cycles (one warp, serial chain): explains the latency-bound regime */
 int kt_fp64_latency(kt_ctx*, double* cycles_per_op);

@@ -7,7 +7,7 @@ library -- that happens on first use and fails loudly if the library or a GPU is
 from . import _abi  # noqa: F401
 from .api import (  # noqa: F401
     Context, DiscWithISCODestination, FlatDiscDestination, FlatPlaneDestination, ImagePlane, ImagePlaneBundles,
-    Integrator, PointSource, RayDestination, Raytracer, disc_image, emissivity, emissivity_bins, emissivity_dev,
+    Integrator, PointSource, RayDestination, Raytracer, TextOutput, caustic_discplane, disc_image, emissivity, emissivity_bins, emissivity_dev,
     get_context, image_bins, imageplane_desc, kerr_horizon, kerr_isco, plane_rays, pointsource_desc,
 )
 from .lib import KerrtraceError  # noqa: F401

@@ -722,6 +722,16 @@ __global__ void k_selftest_divsqrt(unsigned long long* out, unsigned long long s
                                               0x7ff8000000000000ull, 1ull, 0x000fffffffffffffull, 0x7fefffffffffffffull};
             if (i & 8) ua = sp[next() & 7]; else ub = sp[next() & 7];
         }
+        if (mode == 3) {            // kt_sincos_cuda vs sincos(): arguments a ray can have (|x| < 64) and a wide range (|x| < 2^30)
+            const double u = (double)(ua >> 11) * (1.0 / 9007199254740992.0) - 0.5;      // [-0.5, 0.5)
+            const double x = (i & 1) ? u * 128.0 : u * 2147483648.0;
+            double s0, c0, s1, c1;
+            sincos(x, &s0, &c0);
+            kt_sincos_cuda(x, &s1, &c1);
+            if (__double_as_longlong(s0) != __double_as_longlong(s1)) bad_d++;
+            if (__double_as_longlong(c0) != __double_as_longlong(c1)) bad_s++;
+            continue;
+        }
         const double a = __longlong_as_double((long long)ua), b = __longlong_as_double((long long)ub);
         bool ok = true;
         const double q = xdiv(a, b, ok);
@@ -778,9 +788,9 @@ static cudaError_t launch_trace_any(const LaunchCfg& cfg, const TraceParams& P, 
     if (P.integrator == KT_EULER) return launch_trace<KT_EULER, IO, 5>(cfg, P, io, extra_smem);
     if (P.integrator == KT_RK45) {
         if (minb == 3) return launch_trace<KT_RK45, IO, 3>(cfg, P, io, extra_smem);
-        if (minb == 5) return launch_trace<KT_RK45, IO, 5>(cfg, P, io, extra_smem);
         if (minb == 6) return launch_trace<KT_RK45, IO, 6>(cfg, P, io, extra_smem);
-        return launch_trace<KT_RK45, IO, 4>(cfg, P, io, extra_smem);
+        if (minb == 4) return launch_trace<KT_RK45, IO, 4>(cfg, P, io, extra_smem);
+        return launch_trace<KT_RK45, IO, 5>(cfg, P, io, extra_smem);   // measured best of 4 / 5 / 6 (kt_trace.cuh: KT_RK45_CALL note)
     }
     if (minb == 3) return launch_trace<KT_RK4, IO, 3>(cfg, P, io, extra_smem);
     if (minb == 4) return launch_trace<KT_RK4, IO, 4>(cfg, P, io, extra_smem);

@@ -158,7 +158,11 @@ def main():
         obj = os.path.join(tmp, "minifits.o")
         subprocess.run(["/usr/bin/gcc", "-O2", "-c", os.path.join(minifits, "minifits.c"), "-o", obj], check=True)
         for app, src_file, imp in (("imageplane_disc_image", "imageplane/imageplane_disc_image.cpp", "imageplane.cpp"),
-                                   ("caustic_discplane", "caustic/caustic_discplane.cpp", "imageplane.cpp")):
+                                   ("caustic_discplane", "caustic/caustic_discplane.cpp", "imageplane.cpp"),
+                                   ("caustic_plane", "caustic/caustic_plane.cpp", "imageplane.cpp"),
+                                   ("caustic_sourceplane", "caustic/caustic_sourceplane.cpp", "imageplane.cpp")):
+            if not any(missing(parname + ".fits") for parname in APP_PARS[app]):
+                continue
             exe = os.path.join(tmp, app)
             subprocess.run(["/usr/bin/g++", "-O2", "-fopenmp", "-ffp-contract=off", "-w", f"-I{REF}/src", f"-I{REF}/src/raytracer",
                             f"-I{minifits}", f"{REF}/src/{src_file}", f"{REF}/src/raytracer/raytracer.cpp",

@@ -12,7 +12,7 @@ def read_fits(path):
     while pos < len(raw):
         header, done = {}, False
         while not done:
-            block = raw[pos:pos + 2880].decode("ascii")
+            block = raw[pos:pos + 2880].decode("ascii", "replace")
             pos += 2880
             for i in range(0, 2880, 80):
                 card = block[i:i + 80]

@@ -99,6 +99,16 @@ APP_PARS = {
         "app_image_rk4": "dist = 10000\nincl = 30\nspin = 0.998\nr_disc = 30\nx0 = -30\nxmax = 30\ny0 = -30\nymax = 30\n"
                          "Nx = 48\nimg_Nx = 48\nq1 = 3\nrb1 = 4\nq2 = 3\nrb2 = 10\nq3 = 3\nintegrator = rk4\nshow_progress = 0\n",
     },
+    # the sibling caustic applications: a flat source plane behind the hole (FlatPlaneDestination, bundles) and
+    # the celestial sphere (theta_max = 0 disables the theta stop, custom steplim; caustic_sourceplane.cpp:155)
+    "caustic_plane": {
+        "app_caustic_plane_rk4": "dist = 500\nincl = 60\nplane_phi0 = 0\nspin = 0.998\nz_s = 50\nr_max = 600\nx0 = -12\nxmax = 12\nNx = 24\n"
+                                 "integrator = rk4\nprecision = 100\nshow_progress = 0\nbundle_eps_frac = 0.01\n",
+    },
+    "caustic_sourceplane": {
+        "app_caustic_sourceplane_rk4": "dist = 300\nincl = 60\nplane_phi0 = 0\nspin = 0.998\nx0 = -12\nxmax = 12\nNx = 25\n"
+                                       "integrator = rk4\nprecision = 100\nshow_progress = 0\nsteplim = 20000\n",
+    },
     # src/ray_paths/trace_rays.cpp, trace_rays_imageplane.cpp: Euler + outfile (text: t x y z per written point)
     "trace_rays": {
         "app_trace_rays": "source = 0 5 1E-3 0\nV = 0\nspin = 0.998\ndcosalpha = 0.4\ndbeta = 0.9\nr_max = 60\nshow_progress = 0\n"

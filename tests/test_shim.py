@@ -259,3 +259,35 @@ def test_reference_caustic_discplane_app_on_the_gpu(case, n):
     # amplify the per-ray differences by ~1/eps
     assert close_fraction(got["DET_J"], want["DET_J"], 1e-3 if rk45 else 1e-6, both) >= (0.90 if rk45 else 0.96)
     assert (got["SIGN_J"] == want["SIGN_J"])[both].mean() >= 0.97
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(BUILT, "caustic_plane")), reason="shim/_built not present")
+@pytest.mark.parametrize("app,case,n", [("caustic_plane", "app_caustic_plane_rk4", 25), ("caustic_sourceplane", "app_caustic_sourceplane_rk4", 26)])
+def test_reference_sibling_caustic_apps_on_the_gpu(app, case, n):
+    """caustic_plane.cpp (FlatPlaneDestination behind the hole, ray bundles) and caustic_sourceplane.cpp (theta_max = 0,
+    custom steplim, caustic_sourceplane.cpp:155), unchanged: SURVEY 8f.2.  Same extensions, same pixels as the FITS files of the
+    reference's CPU build."""
+    from fits_reader import by_extname, read_fits
+    from golden_cases import APP_PARS
+    want = by_extname(read_fits(os.path.join(GOLDEN, case + ".fits")))
+    with tempfile.TemporaryDirectory() as tmp:
+        prim, got = run_app(app, APP_PARS[app][case], tmp)
+    assert list(got) == list(want) and len(want) == 8
+    hit_name = "HIT_PLANE" if app == "caustic_plane" else "ESCAPED"
+    coords = ("X_S", "Y_S") if app == "caustic_plane" else ("THETA_S", "PHI_S")
+    keep = np.ones((n, n), dtype=bool)
+    keep[n // 2 if n % 2 else slice(0, 0), :] = False          # the y = 0 row exists only on odd grids
+    assert want[hit_name].sum() > 0.5 * n * n
+    assert (got[hit_name] != want[hit_name])[keep].mean() <= 0.01
+    both = (got[hit_name] > 0) & (want[hit_name] > 0) & keep
+    for name in coords:
+        assert close_fraction(got[name], want[name], 1e-9, both) >= 0.98, name
+    assert (got["ORDER"] == want["ORDER"])[both].mean() >= 0.98
+    assert (got["RDOT_FLIPS"] == want["RDOT_FLIPS"])[both].mean() >= 0.98
+    # det(J): bundles differentiate over 1 % of a pixel (amplification ~ 1/eps), the source-plane app over grid neighbours
+    tol = 1e-6 if app == "caustic_plane" else 1e-8
+    defined = both & np.isfinite(want["DET_J"]) & np.isfinite(got["DET_J"]) & (want["DET_J"] < 1e29) & (got["DET_J"] < 1e29)
+    assert defined.sum() > 0.3 * n * n
+    assert close_fraction(got["DET_J"], want["DET_J"], tol, defined) >= 0.95
+    assert (got["SIGN_J"] == want["SIGN_J"])[both].mean() >= 0.97
