@@ -258,7 +258,8 @@ extern "C" int kt_aborted(kt_ctx* c)
 extern "C" void* kt_host_alloc(size_t bytes)
 {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    // mapped + portable: every device of the process can address it, which is what lets kt_trace run zero-copy on it
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
         cudaGetLastError();
         fail(KT_ERR_NOMEM, "pinned allocation of %zu bytes failed", bytes);
         return nullptr;
@@ -1037,6 +1038,10 @@ extern "C" int kt_caustic_discplane(kt_ctx* c, const kt_imageplane* p, const kt_
     if (cfg->img_Nx <= 0 || cfg->img_Ny <= 0) return fail(KT_ERR_INVALID, "bad map size %d x %d", cfg->img_Nx, cfg->img_Ny);
     const long long count = kt_imageplane_count(p, nullptr, nullptr);
     const long long npix = (long long)cfg->img_Nx * cfg->img_Ny;
+    // one block of the context's scratch buffer (it only ever grows: no cudaMalloc / cudaFree per call): 8 double maps (the 7
+    // outputs + the sign snapshot), 2 int maps, 7 counters
+    const size_t bytes = (size_t)npix * (8 * sizeof(double) + 2 * sizeof(int)) + 8 * sizeof(unsigned long long);
+    if (int rc = ensure_scratch(c, bytes)) return rc;
     PlaneFrame F;
     if (count > 0) {
         if (int rc = dev_plane_rays(c, p, tr, stop, run, cfg->redshift_mode, cfg->V, 0, F, count)) return rc;
@@ -1044,13 +1049,9 @@ extern "C" int kt_caustic_discplane(kt_ctx* c, const kt_imageplane* p, const kt_
         make_plane_frame(F, p);
     }
     const long long live = (long long)F.Nx * F.Ny * (F.bundles ? 5 : 1);
-    // one allocation: 8 double maps (the 7 outputs + the sign snapshot), 2 int maps, 7 counters
-    DevBuf buf;
-    const size_t bytes = (size_t)npix * (8 * sizeof(double) + 2 * sizeof(int)) + 8 * sizeof(unsigned long long);
-    if (int rc = buf.alloc(bytes)) return rc;
-    KT_CUDA(cudaMemsetAsync(buf.p, 0, bytes, c->stream));
+    KT_CUDA(cudaMemsetAsync(c->d_scratch, 0, bytes, c->stream));
     CausticMaps m;
-    double* dp = static_cast<double*>(buf.p);
+    double* dp = c->d_scratch;
     m.det_J = dp; m.sign_J = dp + npix; m.radius = dp + 2 * npix; m.phi = dp + 3 * npix; m.x_disc = dp + 4 * npix;
     m.y_disc = dp + 5 * npix; m.redshift = dp + 6 * npix; m.sign_snap = dp + 7 * npix;
     m.cnt = reinterpret_cast<unsigned long long*>(dp + 8 * npix);
