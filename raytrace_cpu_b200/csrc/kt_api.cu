@@ -361,6 +361,20 @@ static int make_params(TraceParams& P, const kt_tracer* tr, const kt_stop* stop,
         const double gap = r_ph - tr->horizon;
         P.stuck_eps = gap > 0 ? 1e-4 * gap : 0.0;
     }
+    // reciprocals of the per-run constant divisors (kt_types.h): usable when the divisor is an ordinary number whose
+    // significand is not all ones
+    {
+        auto usable = [](double b) {
+            uint64_t u;
+            memcpy(&u, &b, sizeof(u));
+            const int e = (int)((u >> 52) & 0x7ff) - 1023;
+            return std::isfinite(b) && b != 0 && e > -200 && e < 200 && (u & 0xfffffffffffffull) != 0xfffffffffffffull;
+        };
+        P.inv_precision = 1.0 / tr->precision;
+        P.inv_theta_precision = 1.0 / tr->theta_precision;
+        P.inv_six = 1.0 / 6.0;
+        P.divc_ok = usable(tr->precision) && usable(tr->theta_precision);
+    }
     P.a = a;
     P.two_a = 2 * a;
     P.two_a_a = 2 * a * a;

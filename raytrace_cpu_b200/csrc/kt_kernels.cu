@@ -722,6 +722,17 @@ __global__ void k_selftest_divsqrt(unsigned long long* out, unsigned long long s
                                               0x7ff8000000000000ull, 1ull, 0x000fffffffffffffull, 0x7fefffffffffffffull};
             if (i & 8) ua = sp[next() & 7]; else ub = sp[next() & 7];
         }
+        if (mode == 4) {            // xdivc: constant divisors with host-style reciprocals, |a| over 2^-700 .. 2^700
+            const double divisors[8] = {6.0, 100.0, 50.0, 3.0, 1000.0, 0.7, 1e-3, 12345.678};
+            const double b = divisors[i & 7];
+            const double y = 1.0 / b;
+            const double a = __longlong_as_double((long long)((ua & 0x800fffffffffffffull) | ((unsigned long long)(1023 - 700 + (ub % 1401)) << 52)));
+            bool ok = true;
+            const double q = xdivc(a, b, y, ok);
+            if (!ok) rej_d++;
+            else if (__double_as_longlong(q) != __double_as_longlong(a / b)) bad_d++;
+            continue;
+        }
         if (mode == 3) {            // kt_sincos_cuda vs sincos(): arguments a ray can have (|x| < 64) and a wide range (|x| < 2^30)
             const double u = (double)(ua >> 11) * (1.0 / 9007199254740992.0) - 0.5;      // [-0.5, 0.5)
             const double x = (i & 1) ? u * 128.0 : u * 2147483648.0;

@@ -15,6 +15,12 @@ struct TraceParams {
     int integrator;
     // loop invariants pre-multiplied exactly as the reference's expressions associate: 2*a, (2*a)*a, a*a
     double a, two_a, two_a_a, aa;
+    // x / precision, x / theta_precision and step / 6 divide by per-run constants: with y = RN(1/b) from the host's IEEE
+    // division, q = RN(x*y), r = x - b*q (exact, one FMA), q' = RN(q + r*y) is the correctly rounded quotient (Markstein's
+    // theorem; b's significand must not be all ones) -- 3 FP64 operations instead of 8 and no special-case frame.
+    // divc_ok == 0 (odd divisors): the plain operator is used.  kt_device.cuh: xdivc
+    double inv_precision, inv_theta_precision, inv_six;
+    int divc_ok;
     double stuck_eps;   // KT_RUN_RETIRE_STUCK: retire ingoing RK45 rays with r - horizon < stuck_eps (0 = off)
     // work queue
     unsigned long long* queue;

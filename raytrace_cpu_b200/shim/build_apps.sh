@@ -22,6 +22,12 @@ mkdir "$OVL/src/raytracer"
 ln -s "$HERE/raytracer"/*.h "$OVL/src/raytracer/"
 FLAGS="-O2 -fopenmp -w -I$OVL/src -I$REPO/include -L$REPO/raytrace_cpu_b200 -Wl,-rpath,$REPO/raytrace_cpu_b200"
 $CXX $FLAGS "$OVL/src/emissivity/emissivity_rd.cpp" -o "$OUT/emissivity_rd" -lkerrtrace
+# emissivity.cpp (the RK45 flagship app) does not compile upstream either: line 79 adds a double to a pointer
+# (`disc_r + dr`).  The overlay holds a build-time copy with upstream's own one-token fix from emissivity_rd.cpp:88 (`dr`);
+# nothing else differs and nothing is committed.
+rm "$OVL/src/emissivity/emissivity.cpp"
+sed 's/disc_r\[ir\]\*dr : disc_r + dr, spin)/disc_r[ir]*dr : dr, spin)/' "$REF/src/emissivity/emissivity.cpp" > "$OVL/src/emissivity/emissivity.cpp"
+$CXX $FLAGS "$OVL/src/emissivity/emissivity.cpp" -o "$OUT/emissivity" -lkerrtrace
 $CXX $FLAGS "$OVL/src/tests/emissivity_rk45_test.cpp" -o "$OUT/emissivity_rk45_test" -lkerrtrace
 $CXX $FLAGS "$OVL/src/tests/integrator_perf_test.cpp" -o "$OUT/integrator_perf_test" -lkerrtrace
 # Euler (the reference's own Euler-vs-RK4 consistency test) and the ray-path dumping applications (Euler + outfile)

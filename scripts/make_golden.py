@@ -122,6 +122,22 @@ def main():
             subprocess.run([exe], check=True, stdout=subprocess.DEVNULL, cwd=os.path.join(tmp, "bin"))
             print("emissivity_rd_app.dat:", sum(1 for _ in open(out)), "lines")
 
+        # emissivity.cpp with upstream's one-token fix of line 79 (build-time sed, as shim/build_apps.sh does)
+        if missing("app_emissivity_rk45.dat"):
+            fixed = os.path.join(tmp, "emissivity_fixed.cpp")
+            text = open(f"{REF}/src/emissivity/emissivity.cpp").read()
+            assert text.count("disc_r[ir]*dr : disc_r + dr, spin)") == 1
+            open(fixed, "w").write(text.replace("disc_r[ir]*dr : disc_r + dr, spin)", "disc_r[ir]*dr : dr, spin)"))
+            exe = os.path.join(tmp, "emissivity")
+            subprocess.run(["/usr/bin/g++", "-O2", "-fopenmp", "-ffp-contract=off", "-w", f"-I{REF}/src", f"-I{REF}/src/raytracer",
+                            f"-I{REF}/src/emissivity", fixed, f"{REF}/src/raytracer/raytracer.cpp", f"{REF}/src/raytracer/pointsource.cpp",
+                            "-o", exe], check=True)
+            out = os.path.join(GOLDEN, "app_emissivity_rk45.dat")
+            with open(os.path.join(tmp, "par", "emissivity.par"), "w") as f:
+                f.write(f"outfile = {out}\n" + APP_PARS["emissivity"]["app_emissivity_rk45"])
+            subprocess.run([exe], check=True, stdout=subprocess.DEVNULL, cwd=os.path.join(tmp, "bin"))
+            print("app_emissivity_rk45.dat:", sum(1 for _ in open(out)), "lines")
+
         # the reference's own Euler-vs-RK4 consistency test (stdout) and its ray-path dumping applications (text files)
         if missing("raytrace_rk4_test.stdout"):
             exe = os.path.join(tmp, "raytrace_rk4_test")

@@ -99,6 +99,12 @@ APP_PARS = {
         "app_image_rk4": "dist = 10000\nincl = 30\nspin = 0.998\nr_disc = 30\nx0 = -30\nxmax = 30\ny0 = -30\nymax = 30\n"
                          "Nx = 48\nimg_Nx = 48\nq1 = 3\nrb1 = 4\nq2 = 3\nrb2 = 10\nq3 = 3\nintegrator = rk4\nshow_progress = 0\n",
     },
+    # emissivity.cpp, the RK45 flagship (BASELINE config 3 geometry, r = 5): built from upstream's source with its own
+    # one-token fix of line 79 -- CPU build for the golden file, shim build for the GPU run
+    "emissivity": {
+        "app_emissivity_rk45": "source = 0 5 1E-3 0\nV = 0\nspin = 0.998\ndcosalpha = 0.02\ndbeta = 0.02\nNr = 30\nlogbin_r = 1\n"
+                               "show_progress = 0\ncosalpha0 = -0.995\ncosalphamax = 0.995\n",
+    },
     # the sibling caustic applications: a flat source plane behind the hole (FlatPlaneDestination, bundles) and
     # the celestial sphere (theta_max = 0 disables the theta stop, custom steplim; caustic_sourceplane.cpp:155)
     "caustic_plane": {
