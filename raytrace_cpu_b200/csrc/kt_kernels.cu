@@ -795,6 +795,10 @@ static cudaError_t launch_trace(const LaunchCfg& cfg, const TraceParams& P, IO i
 template <class IO>
 static cudaError_t launch_trace_any(const LaunchCfg& cfg, const TraceParams& P, IO io, size_t extra_smem)
 {
+#ifdef KT_DEV_MIN   // developer builds for SASS inspection: only the headline kernel (RK4, fused emissivity) is instantiated
+    if constexpr (std::is_same<IO, EmisIO>::value) return launch_trace<KT_RK4, IO, KT_DEV_MIN>(cfg, P, io, extra_smem);
+    else return cudaErrorNotSupported;
+#else
     const int minb = cfg.min_blocks;
     if (P.integrator == KT_EULER) return launch_trace<KT_EULER, IO, 5>(cfg, P, io, extra_smem);
     if (P.integrator == KT_RK45) {
@@ -818,6 +822,7 @@ static cudaError_t launch_trace_any(const LaunchCfg& cfg, const TraceParams& P, 
 #else
     return launch_trace<KT_RK4, IO, 6>(cfg, P, io, extra_smem);
 #endif
+#endif
 }
 
 static inline unsigned nblocks(long long n, int t) { return (unsigned)((n + t - 1) / t); }
@@ -836,6 +841,9 @@ static cudaError_t l_trace_paths(const LaunchCfg& cfg, const TraceParams& P, kt_
     io.rays = rays; io.counters = counters; io.smem = nullptr;
     io.opts = opts; io.counts = counts; io.offsets = offsets; io.points = points;
     // not a throughput path (ordered text output of a few thousand rays): one spill-free occupancy for all integrators
+#ifdef KT_DEV_MIN
+    return cudaErrorNotSupported;
+#endif
     if (P.integrator == KT_EULER) return launch_trace<KT_EULER, PathIO, 3>(cfg, P, io, 0);
     if (P.integrator == KT_RK45) return launch_trace<KT_RK45, PathIO, 3>(cfg, P, io, 0);
     return launch_trace<KT_RK4, PathIO, 3>(cfg, P, io, 0);
