@@ -262,7 +262,7 @@ int kt_fp64_peak(kt_ctx*, double* tflops);
 int kt_selftest_divsqrt(kt_ctx*, int mode, int samples_per_thread, int64_t* counts);
 /* dependent-issue latency of one DFMA in SM cycles (one warp, serial chain): explains the latency-bound regime */
 int kt_fp64_latency(kt_ctx*, double* cycles_per_op);
-/* tuning: resident 128-thread CTAs per SM the trace kernel is built for (3, 4 or 5; 0 = default).  Also
+/* tuning: resident 128-thread CTAs per SM the trace kernel is built for (3, 4, 5 or 6; 0 = the measured best for the integrator and arithmetic mode).  Also
  * read from the environment variable KT_MIN_BLOCKS at kt_create(). */
 int kt_set_min_blocks(kt_ctx*, int min_blocks);
 /* Optional watchdog for the persistent trace kernels (seconds; 0 = off, the default; also read from the

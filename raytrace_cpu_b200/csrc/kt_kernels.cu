@@ -801,26 +801,23 @@ static cudaError_t launch_trace_any(const LaunchCfg& cfg, const TraceParams& P, 
 #else
     const int minb = cfg.min_blocks;
     if (P.integrator == KT_EULER) return launch_trace<KT_EULER, IO, 5>(cfg, P, io, extra_smem);
+    // Defaults = measured best on B200 (1.5e7-ray lamppost runs through the fused kernel, profiles/README.md).  With the guard-free
+    // step the kernel no longer pays for register spills with branch bubbles to hide: the spill-free occupancies win.
+    //   RK4  exact: 3/4/5/6 CTAs of 128 threads per SM -> 358 / 346 / 385 / 385 ms ; fast: 4/5/6 -> 285 / 278 / 281 ms
+    //   RK45 exact (2e6 rays): 3/4/5/6 -> 753 / 876 / 1092 / 1121 ms ; fast: 3/4/5 -> 509 / 521 / 658 ms
     if (P.integrator == KT_RK45) {
-        if (minb == 3) return launch_trace<KT_RK45, IO, 3>(cfg, P, io, extra_smem);
-        if (minb == 6) return launch_trace<KT_RK45, IO, 6>(cfg, P, io, extra_smem);
         if (minb == 4) return launch_trace<KT_RK45, IO, 4>(cfg, P, io, extra_smem);
-        return launch_trace<KT_RK45, IO, 5>(cfg, P, io, extra_smem);   // measured best of 4 / 5 / 6 (kt_trace.cuh: KT_RK45_CALL note)
+        if (minb == 5) return launch_trace<KT_RK45, IO, 5>(cfg, P, io, extra_smem);
+        return launch_trace<KT_RK45, IO, 3>(cfg, P, io, extra_smem);
     }
     if (minb == 3) return launch_trace<KT_RK4, IO, 3>(cfg, P, io, extra_smem);
     if (minb == 4) return launch_trace<KT_RK4, IO, 4>(cfg, P, io, extra_smem);
+    if (minb == 5) return launch_trace<KT_RK4, IO, 5>(cfg, P, io, extra_smem);
     if (minb == 6) return launch_trace<KT_RK4, IO, 6>(cfg, P, io, extra_smem);
-    if constexpr (std::is_same<IO, EmisIO>::value) {   // occupancy experiments on the headline kernel only
-        if (minb == 7) return launch_trace<KT_RK4, IO, 7>(cfg, P, io, extra_smem);
-        if (minb == 8) return launch_trace<KT_RK4, IO, 8>(cfg, P, io, extra_smem);
-    }
-    // default = measured best on B200 (15e6-ray lamppost runs, profiles/README.md): the kernel is bound by FP64
-    // dependency latency (DFMA: 8 cycles), so resident warps beat spill-free registers --
-    //   exact: 4/5/6/7/8 CTAs per SM -> 2.68 / 2.91 / 3.04 / 2.99 / 2.43 e7 rays/s ; fast: 4.37 / 4.67 / 4.67 / 4.56 / 4.61 e7
 #if KT_FAST
     return launch_trace<KT_RK4, IO, 5>(cfg, P, io, extra_smem);
 #else
-    return launch_trace<KT_RK4, IO, 6>(cfg, P, io, extra_smem);
+    return launch_trace<KT_RK4, IO, 4>(cfg, P, io, extra_smem);
 #endif
 #endif
 }
