@@ -39,7 +39,7 @@ METRIC = "rays/sec (lamppost emissivity, a=0.998)"
 def profiled_dram_traffic(math):
     """dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel from the committed ncu --set full capture
     (profiles/, one launch of 1.5e7 rays); None if the summary is missing."""
-    path = os.path.join(ROOT, "profiles", f"r1b_emis_rk4_{math}.txt")
+    path = os.path.join(ROOT, "profiles", f"r1c_emis_rk4_{math}.txt")
     try:
         total, unit = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         for line in open(path):
@@ -59,7 +59,7 @@ def hbm_view(traffic_bytes):
     except Exception:
         peak, src = 6650.0, "fallback (B200_PROFILING.md)"
     return {"peak_gbs": peak, "peak_source": src, "dram_bytes_profiled_launch": traffic_bytes,
-            "note": "profiled launch: 1.5e7 rays in ~0.5 s -> ~0.04 GB/s, 1e-5 of the HBM roofline: the kernel is FP64-bound"}
+            "note": "profiled launch: 1.5e7 rays in ~0.35 s -> ~0.05 GB/s, 1e-5 of the HBM roofline: the kernel is FP64-bound"}
 
 
 def grid_for(total_rays, n_beta=10000):
@@ -417,7 +417,7 @@ def main():
                 "bound": "fp64", "achieved": alg_tflops, "peak": peak_tflops, "unit": "TFLOP/s", "frac": alg_tflops / peak_tflops,
                 "traffic": profiled_dram_traffic(args.math),
                 "traffic_note": "DRAM bytes (read + write) of ONE launch of this kernel on 1.5e7 rays from the committed ncu --set full "
-                                "capture (profiles/r1b_emis_rk4_*.txt): the kernel has no input or output arrays, the few MB are "
+                                "capture (profiles/r1c_emis_rk4_*.txt): the kernel has no input or output arrays, the few MB are "
                                 "register spills evicted from L2; algorithmic HBM traffic is the 4 KB histogram",
                 "how": f"achieved = {FLOP_PER_RK4_STEP:.0f} algorithmic FP64 flop per RK4 step (SURVEY 8d) x {steps_per_step // world} steps "
                        f"per launch / {kernel_ms:.1f} ms (CUDA events around the fused kernel, mean over timed steps, max over ranks); "
