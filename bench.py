@@ -249,9 +249,12 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly one JSON line: while the benchmark runs, file descriptor 1 points at stderr, so that whatever a
+    # library writes there (NCCL prints its version on communicator creation) cannot precede the line; restored before printing
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries exactly one JSON line: whatever NCCL_DEBUG level the box sets, NCCL's own lines go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     ctx = K.get_context(local_rank)
@@ -431,7 +434,10 @@ def main():
             "cpu_baseline": cpu,
             "other_math_mode": other,
         }
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
