@@ -1,5 +1,6 @@
 #!/bin/bash
-# GPU session: full GPU test suite, bench.py, ncu launch list and full captures (raw + per-instruction pages exported as CSV).
+# One GPU session that produces everything profiles/ holds: the GPU test suite, bench.py, the ncu launch list and the full captures
+# (raw + per-instruction source pages exported as CSV on the box; feed the .ncu-rep files to scripts/summarise_ncu.py).
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
