@@ -41,6 +41,16 @@ def test_every_declared_symbol_is_exported():
     assert not [f for f in declared if f not in lib.EXPORTS], "lib.EXPORTS is out of date"
 
 
+def test_cold_path_test_build_exports_the_same_abi():
+    """libkerrtrace_cold.so (csrc/Makefile: cold -- every guard-free quotient / root forced onto its out-of-line recomputation) is
+    what test_parity_gpu.py::test_cold_paths_are_bit_identical runs against the default build: it must exist and be a drop-in."""
+    cold = os.path.join(os.path.dirname(lib.LIB_PATH), "libkerrtrace_cold.so")
+    assert os.path.exists(cold), "run __graft_entry__.build() first (make -C raytrace_cpu_b200/csrc all cold)"
+    syms = subprocess.run(["nm", "-D", "--defined-only", cold], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (kt_[a-z0-9_]+)", syms))
+    assert not [f for f in declared_functions() if f not in exported]
+
+
 def test_no_torch_or_cxx_types_in_the_abi():
     src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)   # comments may mention torch streams
     assert "torch" not in src and "std::" not in src and "template" not in src
