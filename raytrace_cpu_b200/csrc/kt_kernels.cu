@@ -19,6 +19,7 @@ struct RaysetIO {
     static constexpr bool DIRECT_RETIRE = true;
     static constexpr bool KEEP_MOM = true;     // Ray::pt..pphi are written back (raytracer.cpp:956-959)
     static constexpr bool PATHS = false;
+    static constexpr bool NEED_PHI = true;
     template <class H> __device__ void setup_paths(H&) {}
     __device__ long long path_first(long long) { return 0; }
     __device__ void path_done(long long, int) {}
@@ -89,6 +90,7 @@ struct RaysetIO {
 // =========================================================================================================
 struct PathIO : RaysetIO {
     static constexpr bool PATHS = true;
+    static constexpr bool NEED_PHI = true;
     kt_path_opts opts;
     long long* counts;
     const long long* offsets;
@@ -114,11 +116,16 @@ __device__ __forceinline__ int final_steps(int steps, int status)
 // =========================================================================================================
 // IO policy 2: PointSource -> emissivity histogram  (emissivity{,_rd}.cpp:88-126 in one kernel)
 // =========================================================================================================
-struct EmisIO {
+// PHI = false: the azimuth is not integrated (RK4).  Nothing in the emissivity reduction reads phi -- the histogram is over r -- so
+// unless the stop surface does (FlatPlaneDestination: ray_destination.h:170-204), its accumulator and update are dropped: 5 FP64
+// instructions and 4 registers per step.
+template <bool PHI>
+struct EmisIOT {
     static constexpr int ND_IN = 5, NI_IN = 3, ND_OUT = 7, NI_OUT = 3;
     static constexpr bool DIRECT_RETIRE = false;
     static constexpr bool KEEP_MOM = false;
     static constexpr bool PATHS = false;
+    static constexpr bool NEED_PHI = PHI;
     template <class H> __device__ void setup_paths(H&) {}
     __device__ long long path_first(long long) { return 0; }
     __device__ void path_done(long long, int) {}
@@ -223,6 +230,7 @@ struct EmisIO {
         }
     }
 };
+using EmisIO = EmisIOT<true>;
 
 // =========================================================================================================
 // IO policy 3: ImagePlane / ImagePlaneBundles -> image maps or compact per-ray results
@@ -236,6 +244,7 @@ struct PlaneIO {
     static constexpr bool DIRECT_RETIRE = false;
     static constexpr bool KEEP_MOM = false;
     static constexpr bool PATHS = false;
+    static constexpr bool NEED_PHI = true;
     template <class H> __device__ void setup_paths(H&) {}
     __device__ long long path_first(long long) { return 0; }
     __device__ void path_done(long long, int) {}
@@ -793,11 +802,30 @@ static cudaError_t launch_trace(const LaunchCfg& cfg, const TraceParams& P, IO i
 }
 
 template <class IO>
+static cudaError_t launch_trace_rk4(const LaunchCfg& cfg, const TraceParams& P, IO io, size_t extra_smem)
+{
+#ifdef KT_DEV_MIN
+    if constexpr (std::is_same<IO, EmisIOT<false>>::value) return launch_trace<KT_RK4, IO, KT_DEV_MIN>(cfg, P, io, extra_smem);
+    else return cudaErrorNotSupported;
+#else
+    const int minb = cfg.min_blocks;
+    if (minb == 3) return launch_trace<KT_RK4, IO, 3>(cfg, P, io, extra_smem);
+    if (minb == 4) return launch_trace<KT_RK4, IO, 4>(cfg, P, io, extra_smem);
+    if (minb == 5) return launch_trace<KT_RK4, IO, 5>(cfg, P, io, extra_smem);
+    if (minb == 6) return launch_trace<KT_RK4, IO, 6>(cfg, P, io, extra_smem);
+#if KT_FAST
+    return launch_trace<KT_RK4, IO, 5>(cfg, P, io, extra_smem);
+#else
+    return launch_trace<KT_RK4, IO, 4>(cfg, P, io, extra_smem);
+#endif
+#endif
+}
+
+template <class IO>
 static cudaError_t launch_trace_any(const LaunchCfg& cfg, const TraceParams& P, IO io, size_t extra_smem)
 {
 #ifdef KT_DEV_MIN   // developer builds for SASS inspection: only the headline kernel (RK4, fused emissivity) is instantiated
-    if constexpr (std::is_same<IO, EmisIO>::value) return launch_trace<KT_RK4, IO, KT_DEV_MIN>(cfg, P, io, extra_smem);
-    else return cudaErrorNotSupported;
+    return cudaErrorNotSupported;
 #else
     const int minb = cfg.min_blocks;
     if (P.integrator == KT_EULER) return launch_trace<KT_EULER, IO, 5>(cfg, P, io, extra_smem);
@@ -810,15 +838,7 @@ static cudaError_t launch_trace_any(const LaunchCfg& cfg, const TraceParams& P, 
         if (minb == 5) return launch_trace<KT_RK45, IO, 5>(cfg, P, io, extra_smem);
         return launch_trace<KT_RK45, IO, 3>(cfg, P, io, extra_smem);
     }
-    if (minb == 3) return launch_trace<KT_RK4, IO, 3>(cfg, P, io, extra_smem);
-    if (minb == 4) return launch_trace<KT_RK4, IO, 4>(cfg, P, io, extra_smem);
-    if (minb == 5) return launch_trace<KT_RK4, IO, 5>(cfg, P, io, extra_smem);
-    if (minb == 6) return launch_trace<KT_RK4, IO, 6>(cfg, P, io, extra_smem);
-#if KT_FAST
-    return launch_trace<KT_RK4, IO, 5>(cfg, P, io, extra_smem);
-#else
-    return launch_trace<KT_RK4, IO, 4>(cfg, P, io, extra_smem);
-#endif
+    return launch_trace_rk4(cfg, P, io, extra_smem);
 #endif
 }
 
@@ -849,11 +869,19 @@ static cudaError_t l_trace_paths(const LaunchCfg& cfg, const TraceParams& P, kt_
 static cudaError_t l_trace_emis(const LaunchCfg& cfg, const TraceParams& P, const PointSourceFrame& F, const kt_emis_bins& B,
                                 double log_dr, double* hist)
 {
+    const size_t hist_bytes = (size_t)5 * B.Nr * sizeof(double);
+    const bool smem_hist = hist_bytes <= 64 * 1024;
+    // RK4 towards anything but a FlatPlaneDestination: nothing reads phi, so it is not integrated (EmisIOT<false>)
+    if (P.integrator == KT_RK4 && P.stop.kind != KT_STOP_FLATPLANE) {
+        EmisIOT<false> io;
+        io.F = F; io.B = B; io.log_dr = log_dr; io.hist = hist; io.smem = nullptr;
+        io.use_smem_hist = smem_hist;
+        return launch_trace_rk4(cfg, P, io, smem_hist ? hist_bytes : 0);
+    }
     EmisIO io;
     io.F = F; io.B = B; io.log_dr = log_dr; io.hist = hist; io.smem = nullptr;
-    const size_t hist_bytes = (size_t)5 * B.Nr * sizeof(double);
-    io.use_smem_hist = hist_bytes <= 64 * 1024;
-    return launch_trace_any(cfg, P, io, io.use_smem_hist ? hist_bytes : 0);
+    io.use_smem_hist = smem_hist;
+    return launch_trace_any(cfg, P, io, smem_hist ? hist_bytes : 0);
 }
 
 static cudaError_t l_trace_image(const LaunchCfg& cfg, const TraceParams& P, const PlaneFrame& F, const kt_image_bins& B,
