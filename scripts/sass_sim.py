@@ -2,7 +2,7 @@
 """sass_sim.py -- developer tool: follow the hot path of a kernel through its SASS and estimate how it issues on an SMSP.
 
     cuobjdump -sass -fun <mangled kernel> kt_kernels_exact.o > k.sass
-    python scripts/sass_sim.py k.sass 0x340 [0x420=T ...]      # start address (the main-loop head), branch hints addr=T|N
+    python scripts/sass_sim.py k.sass auto | 0x340 [0x420=T ...]   # start address (the main-loop head), branch hints addr=T|N
 
 trace(): follows instructions from the start address; forward conditional branches are not taken unless they skip a short
 block that ends in a CALL or a far jump (cold blocks: slow-path subroutines, early exits), a hint says otherwise, and the walk
@@ -166,13 +166,26 @@ def trace(ins,idx,start,stops,hints,maxn=5000,log=False):
 
 if __name__ == "__main__":
     f = sys.argv[1]
-    start = int(sys.argv[2], 16)
+    ins = parse(f)
+    idx = build(ins)
     hints = {}
+    if sys.argv[2] == "auto":
+        # trace_persistent: the main loop is closed by the last long unconditional backward BRA; the first conditional branch
+        # after its head is the housekeeping vote, taken (no housekeeping) in the steady state
+        back = []
+        for a, t in ins:
+            m = re.search(r"0x([0-9a-f]+)", t)
+            if t.startswith("BRA ") and m and int(m.group(1), 16) < a and (a - int(m.group(1), 16)) // 16 > 800:
+                back.append((a, int(m.group(1), 16)))
+        start = min(b[1] for b in back)
+        first = next(a for a, t in ins if a >= start and t.startswith("@") and "BRA" in t)
+        hints[first] = True
+        print(f"main-loop head {start:#x}, housekeeping vote branch {first:#x}")
+    else:
+        start = int(sys.argv[2], 16)
     for h in sys.argv[3:]:
         k, v = h.split("=")
         hints[int(k, 16)] = (v == "T")
-    ins = parse(f)
-    idx = build(ins)
     prog = trace(ins, idx, start, set(), hints, maxn=4000)
     c = collections.Counter((t.split()[1] if t.startswith("@") else t.split()[0]).split(".")[0] for a, t in prog)
     print(f"{len(prog)} instructions on the path; FP64 {c['DFMA'] + c['DMUL'] + c['DADD']} (+{c['DSETP']} DSETP), MUFU {c['MUFU']}, "
