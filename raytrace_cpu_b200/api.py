@@ -399,6 +399,8 @@ class PointSource(Raytracer):
         self.desc = pointsource_desc(pos, V, dcosalpha, dbeta, cosalpha0, cosalphamax, beta0, betamax, E)
         na, nb = C.c_int32(), C.c_int32()
         n = _lib.load().kt_pointsource_count(C.byref(self.desc), C.byref(na), C.byref(nb))
+        if n < 0:
+            raise KerrtraceError(_lib.load().kt_last_error().decode())
         self.n_cosalpha, self.n_beta = na.value, nb.value
         self.velocity, self.energy = V, E
         super().__init__(n, spin, tol, ctx=ctx, math_mode=math_mode)
@@ -423,6 +425,8 @@ class ImagePlane(Raytracer):
         self.desc = imageplane_desc(dist, inc, x0, xmax, dx, y0, ymax, dy, phi, self._BUNDLES, eps_frac)
         nx, ny = C.c_int32(), C.c_int32()
         n = _lib.load().kt_imageplane_count(C.byref(self.desc), C.byref(nx), C.byref(ny))
+        if n < 0:
+            raise KerrtraceError(_lib.load().kt_last_error().decode())
         self.Nx, self.Ny = nx.value, ny.value
         self.m_x0, self.m_dx, self.m_y0, self.m_dy = x0, dx, y0, dy
         super().__init__(n, -1 * spin, precision, ctx=ctx, math_mode=math_mode)  # imageplane.cpp:12 negates the spin
@@ -584,6 +588,8 @@ def plane_rays(plane, spin, stop, method=Integrator.RK4, r_max=None, precision=A
         stop = stop._stop()
     run = make_run(method, 1.1 * plane.dist if r_max is None else r_max, steplim, math_mode)
     n = ctx.L.kt_imageplane_count(C.byref(plane), None, None)
+    if n < 0:
+        raise KerrtraceError(ctx.L.kt_last_error().decode())
     out = np.zeros(n, dtype=A.RAY_MIN_DTYPE)
     check(ctx.L.kt_imageplane_rays(ctx.h, C.byref(plane), C.byref(tr), C.byref(stop), C.byref(run), redshift_mode, V,
                                    int(range_phi), out.ctypes.data_as(C.c_void_p), n))

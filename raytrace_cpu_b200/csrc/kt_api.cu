@@ -195,7 +195,9 @@ extern "C" void kt_destroy(kt_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    // c->stream may be a caller-owned stream (kt_set_stream) that the caller has already destroyed -- Python finalisers run in
+    // any order at interpreter exit -- so it is never touched here: the whole device is drained instead.
+    cudaDeviceSynchronize();
     if (c->d_queue) cudaFree(c->d_queue);
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->d_rays) cudaFree(c->d_rays);
@@ -316,8 +318,23 @@ extern "C" void kt_tracer_init(kt_tracer* tr, double spin, double precision)
     tr->rk45_tol = 1e-8;
 }
 
+// A grid axis is usable when its step is finite and non-zero and the slot count (lo..hi)/step + 1 is a finite number in
+// [1, 2^31): anything else would cast inf / NaN to an integer on the host and divide by a zero count on the device.
+static bool axis_ok(double lo, double hi, double step)
+{
+    if (!std::isfinite(lo) || !std::isfinite(hi) || !std::isfinite(step) || step == 0) return false;
+    const double f = ((hi - lo) / step) + 1;
+    return std::isfinite(f) && f >= 1 && f < 2147483648.0;
+}
+
 extern "C" int64_t kt_pointsource_count(const kt_pointsource* s, int32_t* n_cosalpha, int32_t* n_beta)
 {
+    if (!s || !axis_ok(s->cosalpha0, s->cosalphamax, s->dcosalpha) || !axis_ok(s->beta0, s->betamax, s->dbeta)) {
+        if (n_cosalpha) *n_cosalpha = 0;
+        if (n_beta) *n_beta = 0;
+        fail(KT_ERR_INVALID, "point-source grid: steps must be finite and non-zero and each axis must hold 1 .. 2^31-1 slots");
+        return -1;
+    }
     const double fa = ((s->cosalphamax - s->cosalpha0) / s->dcosalpha) + 1;
     const double fb = ((s->betamax - s->beta0) / s->dbeta) + 1;
     if (n_cosalpha) *n_cosalpha = (int32_t)fa;
@@ -329,6 +346,12 @@ extern "C" int64_t kt_pointsource_count(const kt_pointsource* s, int32_t* n_cosa
 
 extern "C" int64_t kt_imageplane_count(const kt_imageplane* p, int32_t* Nx, int32_t* Ny)
 {
+    if (!p || !axis_ok(p->x0, p->xmax, p->dx) || !axis_ok(p->y0, p->ymax, p->dy)) {
+        if (Nx) *Nx = 0;
+        if (Ny) *Ny = 0;
+        fail(KT_ERR_INVALID, "image-plane grid: steps must be finite and non-zero and each axis must hold 1 .. 2^31-1 slots");
+        return -1;
+    }
     const double fx = ((p->xmax - p->x0) / p->dx) + 1;
     const double fy = ((p->ymax - p->y0) / p->dy) + 1;
     if (Nx) *Nx = (int32_t)fx;
@@ -383,18 +406,25 @@ static int make_params(TraceParams& P, const kt_tracer* tr, const kt_stop* stop,
     return KT_OK;
 }
 
-static void set_work(TraceParams& P, kt_ctx* c, long long count, const kt_shard* sh)
+static int set_work(TraceParams& P, kt_ctx* c, long long count, const kt_shard* sh)
 {
     P.queue = c->d_queue;
     P.abort_flag = reinterpret_cast<int*>(c->d_queue + 1);
     P.timeout_ns = c->timeout_s > 0 ? (unsigned long long)(c->timeout_s * 1e9) : 0ull;
+    if (count < 0) return fail(KT_ERR_INVALID, "invalid source grid");   // kt_*_count has recorded why
     if (!sh) {
         P.begin = 0; P.end = count; P.rank = 0; P.nranks = 1; P.chunk = 65536; P.n_work = count;
-        return;
+        return KT_OK;
     }
-    long long b = sh->begin < 0 ? 0 : sh->begin;
+    // a shard outside these bounds would make ordinal_to_index produce negative or foreign indices (duplicated / missing rays)
+    const int nr = sh->nranks > 1 ? sh->nranks : 1;
+    if (sh->begin < 0 || sh->end < sh->begin)
+        return fail(KT_ERR_INVALID, "kt_shard: need 0 <= begin <= end (got begin %lld, end %lld)", (long long)sh->begin, (long long)sh->end);
+    if (sh->nranks < 0 || (nr > 1 && (sh->rank < 0 || sh->rank >= nr)))
+        return fail(KT_ERR_INVALID, "kt_shard: need 0 <= rank < nranks (got rank %d of %d)", (int)sh->rank, (int)sh->nranks);
+    if (sh->chunk < 0) return fail(KT_ERR_INVALID, "kt_shard: negative chunk");
+    long long b = sh->begin > count ? count : sh->begin;
     long long e = sh->end > count ? count : sh->end;
-    if (e < b) e = b;
     P.begin = b; P.end = e;
     P.nranks = sh->nranks > 1 ? sh->nranks : 1;
     P.rank = P.nranks > 1 ? sh->rank : 0;
@@ -407,10 +437,11 @@ static void set_work(TraceParams& P, kt_ctx* c, long long count, const kt_shard*
         c = (c / 32) * 32;
         P.chunk = c < 32 ? 32 : (c > 65536 ? 65536 : c);
     }
-    if (P.nranks == 1) { P.n_work = e - b; return; }
+    if (P.nranks == 1) { P.n_work = e - b; return KT_OK; }
     const long long nchunks = (total + P.chunk - 1) / P.chunk;
     const long long mine = nchunks > P.rank ? (nchunks - P.rank + P.nranks - 1) / P.nranks : 0;
     P.n_work = mine * P.chunk;   // upper bound; the kernel drops ordinals that map beyond `end`
+    return KT_OK;
 }
 
 // source-frame tetrad of calculate_constants (raytracer.cpp:632-650), evaluated once on the host with the
@@ -497,7 +528,7 @@ extern "C" void kt_rayset_destroy(kt_rayset* rs)
 {
     if (!rs) return;
     cudaSetDevice(rs->ctx->device);
-    cudaStreamSynchronize(rs->ctx->stream);
+    cudaDeviceSynchronize();   // not the context's stream: it may be a caller-owned stream that no longer exists (see kt_destroy)
     if (rs->d) cudaFree(rs->d);
     delete rs;
 }
@@ -529,6 +560,7 @@ static int dev_init_pointsource(kt_ctx* c, kt_ray* d, long long n, const kt_trac
     if (!s) return fail(KT_ERR_INVALID, "null source");
     TraceParams P;
     if (int rc = make_params(P, tr, nullptr, nullptr)) return rc;
+    if (kt_pointsource_count(s, nullptr, nullptr) < 0) return KT_ERR_INVALID;   // degenerate grid (message recorded)
     PointSourceFrame F;
     make_ps_frame(F, tr, s);
     KT_CUDA(kt_kernel_table_exact()->init_pointsource(cfg_of(c), d, n, P, F));
@@ -541,6 +573,7 @@ static int dev_init_imageplane(kt_ctx* c, kt_ray* d, long long n, const kt_trace
     if (!p) return fail(KT_ERR_INVALID, "null image plane");
     TraceParams P;
     if (int rc = make_params(P, tr, nullptr, nullptr)) return rc;
+    if (kt_imageplane_count(p, nullptr, nullptr) < 0) return KT_ERR_INVALID;    // degenerate grid (message recorded)
     PlaneFrame F;
     make_plane_frame(F, p);
     KT_CUDA(kt_kernel_table_exact()->init_imageplane(cfg_of(c), d, n, P, F));
@@ -573,7 +606,7 @@ static int dev_trace(kt_ctx* c, kt_ray* d, long long n, const kt_tracer* tr, con
     TraceParams P;
     if (int rc = make_params(P, tr, stop, run)) return rc;
     if (n <= 0) return KT_OK;
-    set_work(P, c, n, nullptr);
+    if (int rc = set_work(P, c, n, nullptr)) return rc;
     if (int rc = ensure_scratch(c, KT_NCOUNTERS * sizeof(double))) return rc;
     KT_CUDA(cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned long long), c->stream));
     KT_CUDA(cudaMemsetAsync(c->d_scratch, 0, KT_NCOUNTERS * sizeof(double), c->stream));
@@ -777,7 +810,7 @@ extern "C" int kt_trace(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, con
         memset(&pa, 0, sizeof(pa));
         if (cudaPointerGetAttributes(&pa, rays) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
             TraceParams P = P0;
-            set_work(P, c, n, nullptr);
+            if (int rc = set_work(P, c, n, nullptr)) return rc;
             if (int rc = ensure_scratch(c, KT_NCOUNTERS * sizeof(double))) return rc;
             KT_CUDA(cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned long long), c->stream));
             KT_CUDA(cudaMemsetAsync(c->d_scratch, 0, KT_NCOUNTERS * sizeof(double), c->stream));
@@ -789,52 +822,65 @@ extern "C" int kt_trace(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, con
         cudaGetLastError();   // not a CUDA-visible pointer: staged path
     }
     if (int rc = stage_in(c, rays, n, false)) return rc;
-    KT_CUDA(cudaEventRecord(c->pipe_start, c->stream));
-    for (int i = 0; i < kt_ctx::NPIPE; i++) KT_CUDA(cudaStreamWaitEvent(c->pipe[i], c->pipe_start, 0));
-    KT_CUDA(cudaMemsetAsync(c->d_pipe_cnt, 0, kt_ctx::NPIPE * KT_NCOUNTERS * sizeof(double), c->pipe[0]));
     long long nchunks = n / c->pipe_chunk;
     nchunks = nchunks < 1 ? 1 : (nchunks > kt_ctx::NPIPE ? kt_ctx::NPIPE : nchunks);
     const bool trace_pipe = getenv("KT_PIPE_TRACE") != nullptr;   // developer aid: print the per-chunk timeline
-    cudaEvent_t ev[kt_ctx::NPIPE][4];
-    if (trace_pipe)
-        for (int i = 0; i < kt_ctx::NPIPE; i++)
-            for (int j = 0; j < 4; j++) cudaEventCreate(&ev[i][j]);
+    cudaEvent_t ev[kt_ctx::NPIPE][4] = {};
     const long long chunk = ((n + nchunks - 1) / nchunks + 31) / 32 * 32;
     int k = 0;
-    for (long long off = 0; off < n; off += chunk, k++) {
-        const long long len = (n - off < chunk) ? (n - off) : chunk;
-        const int si = k % kt_ctx::NPIPE;
-        cudaStream_t st = c->pipe[si];
-        kt_ray* d = c->d_rays + off;
-        if (trace_pipe) cudaEventRecord(ev[si][0], st);
-        KT_CUDA(cudaMemcpyAsync(d, rays + off, (size_t)len * sizeof(kt_ray), cudaMemcpyHostToDevice, st));
-        if (trace_pipe) cudaEventRecord(ev[si][1], st);
-        TraceParams P = P0;
-        set_work(P, c, len, nullptr);
-        P.queue = c->d_pipe_queue + si;
-        KT_CUDA(cudaMemsetAsync(P.queue, 0, sizeof(unsigned long long), st));
-        LaunchCfg cfg = cfg_of(c);
-        cfg.stream = st;
-        KT_CUDA(T->trace_rayset(cfg, P, d, c->d_pipe_cnt + si * KT_NCOUNTERS));
-        c->launches++;
-        if (trace_pipe) cudaEventRecord(ev[si][2], st);
-        KT_CUDA(cudaMemcpyAsync(rays + off, d, (size_t)len * sizeof(kt_ray), cudaMemcpyDeviceToHost, st));
-        if (trace_pipe) cudaEventRecord(ev[si][3], st);
-    }
-    for (int i = 0; i < kt_ctx::NPIPE; i++) {
-        KT_CUDA(cudaEventRecord(c->pipe_done[i], c->pipe[i]));
-        KT_CUDA(cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0));
-    }
-    KT_CUDA(cudaStreamSynchronize(c->stream));
-    if (trace_pipe) {
+    // Everything that can fail after the first asynchronous operation runs inside `enqueue`: whatever it returns, the pipe
+    // streams are drained before this call returns (no D2H copy may still be writing into the caller's array once the caller
+    // has been told the call failed) and the timeline events are destroyed.
+    auto enqueue = [&]() -> int {
+        if (trace_pipe)
+            for (int i = 0; i < kt_ctx::NPIPE; i++)
+                for (int j = 0; j < 4; j++) KT_CUDA(cudaEventCreate(&ev[i][j]));
+        KT_CUDA(cudaEventRecord(c->pipe_start, c->stream));
+        for (int i = 0; i < kt_ctx::NPIPE; i++) KT_CUDA(cudaStreamWaitEvent(c->pipe[i], c->pipe_start, 0));
+        for (long long off = 0; off < n; off += chunk, k++) {
+            const long long len = (n - off < chunk) ? (n - off) : chunk;
+            const int si = k % kt_ctx::NPIPE;
+            cudaStream_t st = c->pipe[si];
+            kt_ray* d = c->d_rays + off;
+            if (trace_pipe) cudaEventRecord(ev[si][0], st);
+            KT_CUDA(cudaMemcpyAsync(d, rays + off, (size_t)len * sizeof(kt_ray), cudaMemcpyHostToDevice, st));
+            if (trace_pipe) cudaEventRecord(ev[si][1], st);
+            TraceParams P = P0;
+            if (int rc = set_work(P, c, len, nullptr)) return rc;
+            P.queue = c->d_pipe_queue + si;
+            // the stream's queue counter and its slice of the statistics are zeroed on the stream that uses them
+            KT_CUDA(cudaMemsetAsync(P.queue, 0, sizeof(unsigned long long), st));
+            KT_CUDA(cudaMemsetAsync(c->d_pipe_cnt + si * KT_NCOUNTERS, 0, KT_NCOUNTERS * sizeof(double), st));
+            LaunchCfg cfg = cfg_of(c);
+            cfg.stream = st;
+            KT_CUDA(T->trace_rayset(cfg, P, d, c->d_pipe_cnt + si * KT_NCOUNTERS));
+            c->launches++;
+            if (trace_pipe) cudaEventRecord(ev[si][2], st);
+            KT_CUDA(cudaMemcpyAsync(rays + off, d, (size_t)len * sizeof(kt_ray), cudaMemcpyDeviceToHost, st));
+            if (trace_pipe) cudaEventRecord(ev[si][3], st);
+        }
+        for (int i = 0; i < kt_ctx::NPIPE; i++) {
+            KT_CUDA(cudaEventRecord(c->pipe_done[i], c->pipe[i]));
+            KT_CUDA(cudaStreamWaitEvent(c->stream, c->pipe_done[i], 0));
+        }
+        KT_CUDA(cudaStreamSynchronize(c->stream));
+        return KT_OK;
+    };
+    const int rc = enqueue();
+    if (rc != KT_OK) {
+        for (int i = 0; i < kt_ctx::NPIPE; i++) cudaStreamSynchronize(c->pipe[i]);
+        cudaGetLastError();
+    } else if (trace_pipe) {
         for (int i = 0; i < k && i < kt_ctx::NPIPE; i++) {
             float t[4];
             for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], ev[0][0], ev[i][j]);
             fprintf(stderr, "kt_trace chunk %d: H2D %.1f-%.1f ms, kernel done %.1f ms, D2H done %.1f ms\n", i, t[0], t[1], t[2], t[3]);
         }
-        for (int i = 0; i < kt_ctx::NPIPE; i++)
-            for (int j = 0; j < 4; j++) cudaEventDestroy(ev[i][j]);
     }
+    for (int i = 0; i < kt_ctx::NPIPE; i++)
+        for (int j = 0; j < 4; j++)
+            if (ev[i][j]) cudaEventDestroy(ev[i][j]);
+    if (rc != KT_OK) return rc;
     return c->timeout_s > 0 ? kt_aborted(c) : KT_OK;
 }
 // ---------------------------------------------------------------------------------------------------------
@@ -870,7 +916,7 @@ static int run_paths(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, const 
     if (int rc = ensure_rays(c, (size_t)n * sizeof(kt_ray))) return rc;
     if (int rc = ensure_scratch(c, KT_NCOUNTERS * sizeof(double))) return rc;
     KT_CUDA(cudaMemcpyAsync(c->d_rays, rays, (size_t)n * sizeof(kt_ray), cudaMemcpyHostToDevice, c->stream));
-    set_work(P, c, n, nullptr);
+    if (int rc = set_work(P, c, n, nullptr)) return rc;
     KT_CUDA(cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned long long), c->stream));
     KT_CUDA(cudaMemsetAsync(c->d_scratch, 0, KT_NCOUNTERS * sizeof(double), c->stream));
     KT_CUDA(table_for(run->math_mode)->trace_paths(cfg_of(c), P, c->d_rays, c->d_scratch, *o, d_counts, d_offsets, d_points));
@@ -968,7 +1014,7 @@ extern "C" int kt_pointsource_emissivity_dev(kt_ctx* c, const kt_pointsource* s,
     PointSourceFrame F;
     make_ps_frame(F, tr, s);
     const long long count = kt_pointsource_count(s, nullptr, nullptr);
-    set_work(P, c, count, sh);
+    if (int rc = set_work(P, c, count, sh)) return rc;
     if (P.n_work <= 0) return KT_OK;
     KT_CUDA(cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned long long), c->stream));
     KT_CUDA(table_for(run->math_mode)->trace_emis(cfg_of(c), P, F, *b, std::log(b->dr), dev_hist));
@@ -998,7 +1044,7 @@ extern "C" int kt_imageplane_image_dev(kt_ctx* c, const kt_imageplane* p, const 
     PlaneFrame F;
     make_plane_frame(F, p);
     const long long count = kt_imageplane_count(p, nullptr, nullptr);
-    set_work(P, c, count, sh);
+    if (int rc = set_work(P, c, count, sh)) return rc;
     if (P.n_work <= 0) return KT_OK;
     KT_CUDA(cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned long long), c->stream));
     KT_CUDA(table_for(run->math_mode)->trace_image(cfg_of(c), P, F, *b, 1, dev_maps));
@@ -1027,7 +1073,7 @@ static int dev_plane_rays(kt_ctx* c, const kt_imageplane* p, const kt_tracer* tr
     TraceParams P;
     if (int rc = make_params(P, tr, stop, run)) return rc;
     make_plane_frame(F, p);
-    set_work(P, c, count, nullptr);
+    if (int rc = set_work(P, c, count, nullptr)) return rc;
     kt_image_bins B;
     memset(&B, 0, sizeof(B));
     B.redshift_mode = redshift_mode;
@@ -1051,6 +1097,7 @@ extern "C" int kt_caustic_discplane(kt_ctx* c, const kt_imageplane* p, const kt_
     if (!p || !stop || !run || !cfg || !out) return fail(KT_ERR_INVALID, "bad arguments");
     if (cfg->img_Nx <= 0 || cfg->img_Ny <= 0) return fail(KT_ERR_INVALID, "bad map size %d x %d", cfg->img_Nx, cfg->img_Ny);
     const long long count = kt_imageplane_count(p, nullptr, nullptr);
+    if (count < 0) return KT_ERR_INVALID;   // degenerate grid (message recorded by kt_imageplane_count)
     const long long npix = (long long)cfg->img_Nx * cfg->img_Ny;
     // one block of the context's scratch buffer (it only ever grows: no cudaMalloc / cudaFree per call): 8 double maps (the 7
     // outputs + the sign snapshot), 2 int maps, 7 counters
@@ -1107,9 +1154,10 @@ extern "C" int kt_imageplane_rays(kt_ctx* c, const kt_imageplane* p, const kt_tr
     PlaneFrame F;
     make_plane_frame(F, p);
     const long long count = kt_imageplane_count(p, nullptr, nullptr);
+    if (count < 0) return KT_ERR_INVALID;   // degenerate grid (message recorded by kt_imageplane_count)
     if (n < count) return fail(KT_ERR_INVALID, "output buffer holds %lld rays, the plane has %lld", (long long)n, count);
-    if (count <= 0) return KT_OK;
-    set_work(P, c, count, nullptr);
+    if (count == 0) return KT_OK;
+    if (int rc = set_work(P, c, count, nullptr)) return rc;
     kt_image_bins B;
     memset(&B, 0, sizeof(B));
     B.redshift_mode = redshift_mode;

@@ -37,6 +37,8 @@ def lamppost_grid(spins, heights, rays_per_point, Nr=100, n_beta=None, method=ap
         bins = api.emissivity_bins(a, Nr=Nr, r_disc=r_disc, gamma=gamma, src=src)
         bins_of[(a, h)] = bins
         count = ctx.L.kt_pointsource_count(api.C.byref(src), None, None)
+        if count < 0:
+            raise api.KerrtraceError(ctx.L.kt_last_error().decode())
         shard = make_shard(count, rank, world) if world > 1 else None
         api.emissivity_dev(src, a, bins, buf[i].data_ptr(), method=method, shard=shard, ctx=ctx, math_mode=math_mode)
     if world > 1:

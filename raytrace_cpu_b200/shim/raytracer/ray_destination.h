@@ -8,6 +8,7 @@
 #include <cmath>
 #include <limits>
 #include <stdexcept>
+#include <typeinfo>
 
 #include "kerrtrace.h"
 
@@ -112,7 +113,13 @@ template <typename T>
 kt_stop stop_of(const RayDestination<T>* dest)
 {
     if (!dest) throw std::runtime_error("kerrtrace: null RayDestination");
-    const kt_stop s = dest->to_kt_stop();
+    // The reference's concrete classes are not final: a user class derived from one of them may override reached(),
+    // step_limit(), velocity() or four_velocity() and would inherit the base class's to_kt_stop().  Only objects whose dynamic
+    // type is EXACTLY one of the three known classes are offloaded; everything else is refused loudly.
+    const std::type_info& ti = typeid(*dest);
+    const bool known = ti == typeid(FlatDiscDestination<T>) || ti == typeid(DiscWithISCODestination<T>) ||
+                       ti == typeid(FlatPlaneDestination<T>);
+    const kt_stop s = known ? dest->to_kt_stop() : kt_stop{-1};
     if (s.kind < 0)
         throw std::runtime_error("kerrtrace: user-defined RayDestination subclasses are not offloaded (only FlatDisc, "
                                  "DiscWithISCO and FlatPlane destinations run on the device)");

@@ -135,6 +135,9 @@ public:
             cout << "Event horizon at " << horizon << endl;
             cout << "Allocating memory (" << nRays * sizeof(Ray<T>) / (1 << 20) << "MB)" << endl;
         }
+        // Create (or look up) the engine context FIRST: kt_create selects KERRTRACE_DEVICE, so the pinned allocation below opens
+        // its CUDA context on that device and not on device 0 (one process per GPU must not touch GPU 0 from every rank).
+        (void)engine();
         // pinned host memory: the copies of every offloaded call then run at full PCIe rate
         rays = static_cast<Ray<T>*>(kt_host_alloc(sizeof(Ray<T>) * (nRays > 0 ? nRays : 1)));
         if (!rays) throw std::bad_alloc();

@@ -143,3 +143,23 @@ def test_product_never_imports_the_oracle():
                 assert "liboracle" not in text and "kerr_oracle" not in text and "oracle_bindings" not in text, os.path.join(dirpath, f)
     deps = subprocess.run(["ldd", lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in deps
+
+
+def test_degenerate_grids_are_refused():
+    """A zero / non-finite grid step (inf-to-int cast on the host, divide by a zero count on the device) or an axis without a
+    single slot makes kt_pointsource_count / kt_imageplane_count return -1 with a message; the entry points then fail."""
+    L = lib.load()
+    na, nb = C.c_int32(7), C.c_int32(7)
+    for kw in (dict(dcos=0.0), dict(dbeta=0.0), dict(dcos=float("nan")), dict(dbeta=float("inf")), dict(dcos=-0.1)):
+        src = ob.make_pointsource([0, 5, 1e-3, 0], kw.get("dcos", 0.05), kw.get("dbeta", 0.05))
+        assert L.kt_pointsource_count(C.byref(src), C.byref(na), C.byref(nb)) == -1, kw
+        assert (na.value, nb.value) == (0, 0)
+        assert b"point-source grid" in L.kt_last_error()
+    ip = ob.make_imageplane(1e4, 30.0, -30, 30, 32)
+    assert L.kt_imageplane_count(C.byref(ip), None, None) == 33 * 33
+    ip.dx = 0.0
+    assert L.kt_imageplane_count(C.byref(ip), C.byref(na), C.byref(nb)) == -1
+    ip.dx = ip.dy
+    ip.dy = float("nan")
+    assert L.kt_imageplane_count(C.byref(ip), None, None) == -1
+    assert b"image-plane grid" in L.kt_last_error()

@@ -321,3 +321,51 @@ def test_reference_emissivity_rk45_flagship_app_on_the_gpu():
     assert full.sum() >= 10
     for col in (3, 4, 5, 6):
         np.testing.assert_allclose(got[full, col], want[full, col], rtol=1e-2)
+
+
+def test_only_the_exact_destination_classes_are_offloaded():
+    """The reference's concrete destinations are not final: a user class derived from one of them may override reached() /
+    step_limit() / four_velocity() and inherits the base class's device descriptor.  stop_of() compares the dynamic type with
+    the three known classes exactly and throws for anything else (before any device call: runs without a GPU)."""
+    prog = r'''
+#include "raytracer/raytracer.h"
+#include "raytracer/ray_destination.h"
+#include <cstdio>
+template <typename T> struct Wavy : public FlatDiscDestination<T> {
+    using FlatDiscDestination<T>::FlatDiscDestination;
+    bool reached(T r, T theta, T phi) const override { return theta >= 1.0 + 0.1 * sin(r); }
+};
+template <typename T> struct Mine : public RayDestination<T> {
+    bool reached(T, T, T) const override { return false; }
+};
+int main() {
+    FlatDiscDestination<double> disc(M_PI_2);
+    DiscWithISCODestination<double> isco(1.24, 50.0, M_PI_2);
+    FlatPlaneDestination<double> plane(0.5, 0.0, 10.0);
+    if (kerrtrace_shim::stop_of<double>(&disc).kind != KT_STOP_FLATDISC) return 1;
+    if (kerrtrace_shim::stop_of<double>(&isco).kind != KT_STOP_ISCODISC) return 2;
+    if (kerrtrace_shim::stop_of<double>(&plane).kind != KT_STOP_FLATPLANE) return 3;
+    int refused = 0;
+    Wavy<double> wavy(M_PI_2);
+    Mine<double> mine;
+    try { kerrtrace_shim::stop_of<double>(&wavy); } catch (const std::runtime_error&) { refused++; }
+    try { kerrtrace_shim::stop_of<double>(&mine); } catch (const std::runtime_error&) { refused++; }
+    try { kerrtrace_shim::stop_of<double>(nullptr); } catch (const std::runtime_error&) { refused++; }
+    std::printf("refused %d\n", refused);
+    return refused == 3 ? 0 : 4;
+}
+'''
+    ref_inc = os.path.join(REF, "src")
+    if not os.path.isdir(os.path.join(ref_inc, "include")):
+        pytest.skip("the shim headers include the reference's kerr.h / text_output.h: reference checkout absent")
+    with tempfile.TemporaryDirectory() as tmp:
+        src = make_overlay(tmp)
+        with open(os.path.join(src, "t.cpp"), "w") as f:
+            f.write(prog)
+        exe = os.path.join(tmp, "t")
+        libdir = os.path.join(ROOT, "raytrace_cpu_b200")
+        p = subprocess.run(["/usr/bin/g++", "-O1", "-w", f"-I{src}", f"-I{ROOT}/include", os.path.join(src, "t.cpp"), "-o", exe,
+                            f"-L{libdir}", f"-Wl,-rpath,{libdir}", "-lkerrtrace"], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr[-3000:]
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 0 and "refused 3" in r.stdout, (r.returncode, r.stdout, r.stderr)
