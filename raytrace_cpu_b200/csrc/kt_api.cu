@@ -397,6 +397,15 @@ static int make_params(TraceParams& P, const kt_tracer* tr, const kt_stop* stop,
         P.inv_theta_precision = 1.0 / tr->theta_precision;
         P.inv_six = 1.0 / 6.0;
         P.divc_ok = usable(tr->precision) && usable(tr->theta_precision);
+        const double tl = P.stop.theta_lim;
+        P.th_mode = tl > 0 ? 1 : (tl < 0 ? 2 : 0);
+        P.tcap_on = tr->max_tstep > 0 && tr->maxtstep_rlim > 0;
+        P.phcap_on = tr->max_phistep > 0;
+        P.cap_num_t = tr->max_tstep > 0 ? tr->max_tstep : 1.0;
+        P.cap_num_ph = tr->max_phistep > 0 ? tr->max_phistep : 1.0;
+        // (+inf limits are fine: their bit patterns order above every finite number; NaNs are not)
+        P.hot_ok = P.divc_ok && P.rlim > 0 && std::isfinite(tr->horizon) && tr->horizon > 0 && !std::isnan(tl) &&
+                   std::isfinite(tr->max_tstep) && std::isfinite(tr->max_phistep) && !std::isnan(tr->maxtstep_rlim);
     }
     P.a = a;
     P.two_a = 2 * a;

@@ -20,6 +20,7 @@ struct RaysetIO {
     static constexpr bool KEEP_MOM = true;     // Ray::pt..pphi are written back (raytracer.cpp:956-959)
     static constexpr bool PATHS = false;
     static constexpr bool NEED_PHI = true;
+    static constexpr bool NEED_INFO = true;    // status bits, rdot_flips and equatorial_crossings are written back
     template <class H> __device__ void setup_paths(H&) {}
     __device__ long long path_first(long long) { return 0; }
     __device__ void path_done(long long, int) {}
@@ -126,6 +127,9 @@ struct EmisIOT {
     static constexpr bool KEEP_MOM = false;
     static constexpr bool PATHS = false;
     static constexpr bool NEED_PHI = PHI;
+    // the histogram reads r, theta, t, the redshift and the terminal class of a ray: its ERGO / NEG_ENERGY bits, radial turning
+    // points and equatorial crossings are unobservable (emissivity.cpp:96-126), so the RK4 step does not evaluate them
+    static constexpr bool NEED_INFO = false;
     template <class H> __device__ void setup_paths(H&) {}
     __device__ long long path_first(long long) { return 0; }
     __device__ void path_done(long long, int) {}
@@ -245,6 +249,9 @@ struct PlaneIO {
     static constexpr bool KEEP_MOM = false;
     static constexpr bool PATHS = false;
     static constexpr bool NEED_PHI = true;
+    // image maps (imageplane_disc_image.cpp:122-161) read r, phi, t, the redshift and status & DEST; the compact per-ray
+    // results of the caustic path carry status, rdot_flips and equatorial_crossings to the host
+    static constexpr bool NEED_INFO = !IMAGE;
     template <class H> __device__ void setup_paths(H&) {}
     __device__ long long path_first(long long) { return 0; }
     __device__ void path_done(long long, int) {}
@@ -772,7 +779,13 @@ __global__ void k_selftest_divsqrt(unsigned long long* out, unsigned long long s
 // =========================================================================================================
 // Launchers
 // =========================================================================================================
-constexpr int TRACE_THREADS = 128;
+// threads per CTA of the persistent kernel.  Occupancy is set by registers per thread (65 536 per SM, allocated per warp in units
+// of 8 per thread): with 128-thread CTAs the resident-warp count moves in steps of 4 (16, 20, 24 warps per SM at 128 / 96 / 80
+// registers); developer builds with -DKT_TRACE_THREADS=32 -DKT_RK4_MINB=17..19 reach the steps in between.
+#ifndef KT_TRACE_THREADS
+#define KT_TRACE_THREADS 128
+#endif
+constexpr int TRACE_THREADS = KT_TRACE_THREADS;
 
 template <int INTEG, class IO, int MINB>
 static cudaError_t launch_trace(const LaunchCfg& cfg, const TraceParams& P, IO io, size_t extra_smem)
@@ -807,6 +820,8 @@ static cudaError_t launch_trace_rk4(const LaunchCfg& cfg, const TraceParams& P, 
 #ifdef KT_DEV_MIN
     if constexpr (std::is_same<IO, EmisIOT<false>>::value) return launch_trace<KT_RK4, IO, KT_DEV_MIN>(cfg, P, io, extra_smem);
     else return cudaErrorNotSupported;
+#elif defined(KT_RK4_MINB)
+    return launch_trace<KT_RK4, IO, KT_RK4_MINB>(cfg, P, io, extra_smem);
 #else
     const int minb = cfg.min_blocks;
     if (minb == 3) return launch_trace<KT_RK4, IO, 3>(cfg, P, io, extra_smem);

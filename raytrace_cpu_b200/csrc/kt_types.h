@@ -21,6 +21,13 @@ struct TraceParams {
     // divc_ok == 0 (odd divisors): the plain operator is used.  kt_device.cuh: xdivc
     double inv_precision, inv_theta_precision, inv_six;
     int divc_ok;
+    // Host-evaluated facts about the run parameters for the exact-mode RK4 step (kt_trace.cuh: rk4_step_v3), whose ordering tests
+    // run on bit patterns and therefore need to know the signs of the constants they compare with:
+    //   hot_ok   : divc_ok, r_max > 0 and horizon > 0, all finite -- otherwise every step takes the plain out-of-line form
+    //   th_mode  : the theta_max loop guard (raytracer.cpp:799): 0 none (theta_max == 0), 1 theta < theta_max, 2 theta > |theta_max|
+    //   tcap_on  : max_tstep > 0 and maxtstep_rlim > 0 (raytracer.cpp:861);  phcap_on : max_phistep > 0 (:865)
+    int hot_ok, th_mode, tcap_on, phcap_on;
+    double cap_num_t, cap_num_ph;   // numerators of the two step caps: max_tstep / max_phistep, or 1 for a disabled cap (kept ordinary)
     double stuck_eps;   // KT_RUN_RETIRE_STUCK: retire ingoing RK45 rays with r - horizon < stuck_eps (0 = off)
     // work queue
     unsigned long long* queue;
