@@ -404,8 +404,12 @@ static int make_params(TraceParams& P, const kt_tracer* tr, const kt_stop* stop,
         P.cap_num_t = tr->max_tstep > 0 ? tr->max_tstep : 1.0;
         P.cap_num_ph = tr->max_phistep > 0 ? tr->max_phistep : 1.0;
         // (+inf limits are fine: their bit patterns order above every finite number; NaNs are not)
-        P.hot_ok = P.divc_ok && P.rlim > 0 && std::isfinite(tr->horizon) && tr->horizon > 0 && !std::isnan(tl) &&
-                   std::isfinite(tr->max_tstep) && std::isfinite(tr->max_phistep) && !std::isnan(tr->maxtstep_rlim);
+        // ... and moderate magnitudes, the premises of the range-propagated acceptance (kt_trace.cuh: rhs_head, rk4_step_v3)
+        auto within = [](double x, int lo, int hi) { return std::isfinite(x) && std::fabs(x) >= std::ldexp(1.0, lo) && std::fabs(x) <= std::ldexp(1.0, hi); };
+        P.hot_ok = P.divc_ok && P.rlim > 0 && tr->horizon > 0 && within(tr->horizon, -20, 20) && !std::isnan(tl) &&
+                   std::isfinite(tr->max_tstep) && std::isfinite(tr->max_phistep) && !std::isnan(tr->maxtstep_rlim) &&
+                   (a == 0 || within(a, -20, 10)) && within(tr->precision, -30, 30) && within(tr->theta_precision, -30, 30) &&
+                   within(P.cap_num_t, -100, 100) && within(P.cap_num_ph, -100, 100);
     }
     P.a = a;
     P.two_a = 2 * a;

@@ -749,6 +749,24 @@ __global__ void k_selftest_divsqrt(unsigned long long* out, unsigned long long s
             else if (__double_as_longlong(q) != __double_as_longlong(a / b)) bad_d++;
             continue;
         }
+        if (mode == 5) {            // ydiv / ysqrt / ydivc (range-propagated acceptance) over the whole domain their callers establish
+            auto with_exp = [&](unsigned long long u, int lo, int hi) {
+                const unsigned long long e = (unsigned long long)(1023 + lo) + next() % (unsigned long long)(hi - lo + 1);
+                return __longlong_as_double((long long)((u & 0x800fffffffffffffull) | (e << 52)));
+            };
+            const double a = with_exp(ua, -840, 700), b = with_exp(ub, -333, 163);
+            bool ok = true;
+            const double q = ydiv(a, b, ok);
+            if (!ok) rej_d++;
+            else if (__double_as_longlong(q) != __double_as_longlong(a / b)) bad_d++;
+            const double sa = fabs(with_exp(ua ^ ub, -500, 740));
+            if (__double_as_longlong(ysqrt(sa)) != __double_as_longlong(sqrt(sa))) bad_s++;
+            const double divisors[8] = {6.0, 100.0, 50.0, 3.0, 1000.0, 0.7, 1e-3, 12345.678};
+            const double c = divisors[i & 7];
+            const double x = with_exp(ub ^ (ua >> 7), -530, 600);
+            if (__double_as_longlong(ydivc(x, c, 1.0 / c)) != __double_as_longlong(x / c)) bad_s++;
+            continue;
+        }
         if (mode == 3) {            // kt_sincos_cuda vs sincos(): arguments a ray can have (|x| < 64) and a wide range (|x| < 2^30)
             const double u = (double)(ua >> 11) * (1.0 / 9007199254740992.0) - 0.5;      // [-0.5, 0.5)
             const double x = (i & 1) ? u * 128.0 : u * 2147483648.0;
@@ -828,11 +846,9 @@ static cudaError_t launch_trace_rk4(const LaunchCfg& cfg, const TraceParams& P, 
     if (minb == 4) return launch_trace<KT_RK4, IO, 4>(cfg, P, io, extra_smem);
     if (minb == 5) return launch_trace<KT_RK4, IO, 5>(cfg, P, io, extra_smem);
     if (minb == 6) return launch_trace<KT_RK4, IO, 6>(cfg, P, io, extra_smem);
-#if KT_FAST
+    // both modes: 5 CTAs of 128 threads per SM (96 registers).  Round 2, exact mode, 1.5e7 rays: 4 / 5 / 6 -> 296 / 291 / 325 ms
+    // (rk4_step_v3 needs ~90 registers: no local-memory traffic inside the loop at 96)
     return launch_trace<KT_RK4, IO, 5>(cfg, P, io, extra_smem);
-#else
-    return launch_trace<KT_RK4, IO, 4>(cfg, P, io, extra_smem);
-#endif
 #endif
 }
 
