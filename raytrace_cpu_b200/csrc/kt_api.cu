@@ -1245,7 +1245,10 @@ extern "C" int kt_selftest_divsqrt(kt_ctx* c, int mode, int samples_per_thread, 
     if (int rc = ctx_bind(c)) return rc;
     if (!counts) return fail(KT_ERR_INVALID, "null output");
     KT_CUDA(cudaMemsetAsync(c->d_scratch, 0, 5 * sizeof(unsigned long long), c->stream));
-    KT_CUDA(kt_kernel_table_exact()->dfma_peak(cfg_of(c), c->d_scratch, -2, mode, samples_per_thread));
+    if (mode >= 100)   // developer self-test of the fast mode's lean right-hand side (kt_kernels.cu: k_selftest_lean); 101: negated spin
+        KT_CUDA(kt_kernel_table_fast()->dfma_peak(cfg_of(c), c->d_scratch, -7, mode == 100 ? 1 : 0, samples_per_thread));
+    else
+        KT_CUDA(kt_kernel_table_exact()->dfma_peak(cfg_of(c), c->d_scratch, -2, mode, samples_per_thread));
     c->launches++;
     unsigned long long h[5];
     KT_CUDA(cudaMemcpyAsync(h, c->d_scratch, sizeof(h), cudaMemcpyDeviceToHost, c->stream));

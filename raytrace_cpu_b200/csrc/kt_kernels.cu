@@ -712,6 +712,49 @@ __global__ void k_dfma_latency(double* out, int iters)
     if (threadIdx.x == 0) { out[0] = (double)(t1 - t0); out[1] = (double)iters * 32.0; out[2] = a; }
 }
 
+#if KT_FAST
+// developer self-test of the lean right-hand side against the reference expressions (momenta()) at random points:
+// out[i] = max relative difference * 2^60 of {pt, pphi, |ptheta|, |pr|, sin^2, cos^2}
+__global__ void k_selftest_lean(unsigned long long* out, unsigned long long seed, int per_thread, double a)
+{
+    unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+    auto next = [&]() {
+        x += 0x9E3779B97F4A7C15ull;
+        unsigned long long z = x;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    auto u01 = [&]() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); };
+    TraceParams P;
+    P.a = a; P.aa = a * a; P.two_a = 2 * a; P.two_a_a = 2 * a * a;
+    unsigned long long worst[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < per_thread; i++) {
+        RayState s;
+        s.k = 1.0; s.h = 20.0 * (u01() - 0.5); s.Q = 300.0 * u01();
+        s.ka = s.k * a; s.ka2 = s.ka * s.ka; s.h2 = s.h * s.h; s.ah = a * s.h; s.Kc = fma(s.h - s.ka, s.h - s.ka, s.Q);
+        const double r = (i & 1) ? 1.2 + 30.0 * u01() : 30.0 + 500.0 * u01();
+        const double th = 0.05 + 3.0 * u01();
+        LeanVals v;
+        lean_rhs<true>(P, s, r, th, v);
+        const Mom m = momenta(P, s.k, s.h, s.Q, s.ka, 1, 1, r, th);
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        const double got[6] = {v.pt, v.pph, v.pth_abs, v.pr_abs, v.s2, 1.0 - v.s2};
+        const double want[6] = {m.pt, m.pph, m.pth, m.pr, sn * sn, cs * cs};
+        for (int j = 0; j < 6; j++) {
+            const double e = fabs(got[j] - want[j]) / fmax(fabs(want[j]), 1e-300);
+            // skip the neighbourhood of turning points, where both forms cancel: |p| tiny relative to its scale
+            if ((j == 2 || j == 3) && fabs(want[j]) < 1e-3 * fabs(m.pt)) continue;
+            const unsigned long long q = (unsigned long long)fmin(e * 1152921504606846976.0, 1.8e19);
+            if (q > worst[j]) worst[j] = q;
+        }
+    }
+    if (worst[5] > worst[4]) worst[4] = worst[5];
+    for (int j = 0; j < 5; j++) atomicMax(&out[j], worst[j]);
+}
+#endif
+
 // Self-test of xdiv / xsqrt (exact mode): random operands over the whole exponent range plus special values.
 // out[0] = divisions where the guard accepted but the result differs from a / b   (must be 0)
 // out[1] = square roots where the guard accepted but the result differs from sqrt(a) (must be 0)
@@ -747,6 +790,18 @@ __global__ void k_selftest_divsqrt(unsigned long long* out, unsigned long long s
             const double q = xdivc(a, b, y, ok);
             if (!ok) rej_d++;
             else if (__double_as_longlong(q) != __double_as_longlong(a / b)) bad_d++;
+            continue;
+        }
+        if (mode == 6) {            // accuracy of the MUFU seeds: out[0] = max |1 - b rcp64h(b)| * 2^40, out[1] = max |1 - x rsq64h(x)^2| * 2^40
+            const double b = __longlong_as_double((long long)((ua & 0x000fffffffffffffull) | (1023ull << 52)));          // [1, 2)
+            const double x = __longlong_as_double((long long)((ub & 0x000fffffffffffffull) | ((1023ull + (i & 1)) << 52))); // [1, 4)
+            double yb, yx;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(yb) : "d"(b));
+            asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(yx) : "d"(x));
+            const double eb = fabs(fma(-b, yb, 1.0)), ex = fabs(fma(-x * yx, yx, 1.0));
+            const unsigned long long sb = (unsigned long long)(eb * 1099511627776.0), sx = (unsigned long long)(ex * 1099511627776.0);
+            if (sb > bad_d) bad_d = sb;
+            if (sx > bad_s) bad_s = sx;
             continue;
         }
         if (mode == 5) {            // ydiv / ysqrt / ydivc (range-propagated acceptance) over the whole domain their callers establish
@@ -789,6 +844,7 @@ __global__ void k_selftest_divsqrt(unsigned long long* out, unsigned long long s
         if (!oks) rej_s++;
         else if (__double_as_longlong(s) != __double_as_longlong(sr) && !(s != s && sr != sr)) bad_s++;
     }
+    if (mode == 6) { atomicMax(&out[0], bad_d); atomicMax(&out[1], bad_s); atomicAdd(&out[4], (unsigned long long)per_thread); return; }
     atomicAdd(&out[0], bad_d); atomicAdd(&out[1], bad_s); atomicAdd(&out[2], rej_d); atomicAdd(&out[3], rej_s);
     atomicAdd(&out[4], (unsigned long long)per_thread);
 #endif
@@ -992,6 +1048,12 @@ static cudaError_t l_caustic_pass(const LaunchCfg& cfg, int pass, const kt_ray_m
 }
 static cudaError_t l_dfma_peak(const LaunchCfg& cfg, double* out, int blocks, int threads, int iters)
 {
+#if KT_FAST
+    if (blocks == -7) { // developer self-test of the lean right-hand side (fast mode only)
+        k_selftest_lean<<<cfg.sm_count * 4, 128, 0, cfg.stream>>>(reinterpret_cast<unsigned long long*>(out), 0x777ull, iters, threads > 0 ? 0.998 : -0.998);
+        return cudaGetLastError();
+    }
+#endif
     if (blocks < -1) {  // self-test of xdiv / xsqrt: threads = sampling mode, iters = samples per thread
         k_selftest_divsqrt<<<cfg.sm_count * 8, 256, 0, cfg.stream>>>(reinterpret_cast<unsigned long long*>(out), 0x1234567ull + threads, iters, threads);
         return cudaGetLastError();

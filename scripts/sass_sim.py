@@ -170,17 +170,18 @@ if __name__ == "__main__":
     idx = build(ins)
     hints = {}
     if sys.argv[2] == "auto":
-        # trace_persistent: the main loop is closed by the last long unconditional backward BRA; the first conditional branch
-        # after its head is the housekeeping vote, taken (no housekeeping) in the steady state
+        # trace_persistent (round 2): the stepping loop is the innermost loop that holds a whole integration step, i.e. the
+        # backward branch with the smallest span above 300 instructions; its first conditional branch skips the step for a lane
+        # without an active ray (not taken in the steady state)
         back = []
         for a, t in ins:
             m = re.search(r"0x([0-9a-f]+)", t)
-            if t.startswith("BRA ") and m and int(m.group(1), 16) < a and (a - int(m.group(1), 16)) // 16 > 800:
-                back.append((a, int(m.group(1), 16)))
-        start = min(b[1] for b in back)
-        first = next(a for a, t in ins if a >= start and t.startswith("@") and "BRA" in t)
-        hints[first] = True
-        print(f"main-loop head {start:#x}, housekeeping vote branch {first:#x}")
+            if "BRA" in t and m and int(m.group(1), 16) < a and (a - int(m.group(1), 16)) // 16 > 300:
+                tgt = int(m.group(1), 16)
+                if any("VOTE" in u for b, u in ins if tgt <= b <= a):     # (the loop's exit vote: rules out loops of cold subroutines)
+                    back.append(((a - tgt) // 16, tgt))
+        start = min(back)[1]
+        print(f"stepping-loop head {start:#x} ({min(back)[0]} instructions to its backward branch)")
     else:
         start = int(sys.argv[2], 16)
     for h in sys.argv[3:]:
