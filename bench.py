@@ -39,7 +39,7 @@ METRIC = "rays/sec (lamppost emissivity, a=0.998)"
 def profiled_dram_traffic(math):
     """dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel from the committed ncu --set full capture
     (profiles/, one launch of 1.5e7 rays); None if the summary is missing."""
-    path = os.path.join(ROOT, "profiles", f"r1c_emis_rk4_{math}.txt")
+    path = os.path.join(ROOT, "profiles", f"r2_emis_rk4_{math}.txt")
     try:
         total, unit = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         for line in open(path):
@@ -59,7 +59,7 @@ def hbm_view(traffic_bytes):
     except Exception:
         peak, src = 6650.0, "fallback (B200_PROFILING.md)"
     return {"peak_gbs": peak, "peak_source": src, "dram_bytes_profiled_launch": traffic_bytes,
-            "note": "profiled launch: 1.5e7 rays in ~0.35 s -> ~0.05 GB/s, 1e-5 of the HBM roofline: the kernel is FP64-bound"}
+            "note": "profiled launch: 1.5e7 rays in ~0.28 s -> ~0.05 GB/s, 1e-5 of the HBM roofline: the kernel is FP64-issue-bound"}
 
 
 def grid_for(total_rays, n_beta=10000):
@@ -346,8 +346,10 @@ def main():
         ocnt = A.EmisResult.from_packed(NR, hist.cpu().numpy()).counters
         other = {"math": oname, "value": int(ocnt[A.CNT_TRACED]) * args.steps / (oms.item() * 1e-3), "unit": "rays/s",
                  "ms_per_step": oms.item() / args.steps, "warmup": 1,
-                 "note": "same workload and timing rules; 'fast' = FMA contraction + shared reciprocals, the arithmetic class of the "
-                         "reference's own -march=native build (0.26 % of rays beyond 1e-9 on the reference's test grid)"}
+                 "note": "same workload and timing rules; 'fast' = the reference's right-hand side evaluated through algebraically "
+                         "equivalent, cheaper expressions with FMA contraction (kt_trace.cuh: rk4_step_lean); same step schedule; "
+                         "per-ray deviations are in the class of the reference's own -march=native build (0.26 % of rays beyond "
+                         "1e-9 on the reference's test grid, the same rays the FMA-contracted reference moves)"}
 
     # ---- end to end through the reference-facing C ABI call with HOST buffers (kt_trace on Ray<double>[]) ----
     e2e = None
@@ -422,12 +424,16 @@ def main():
                 "bound": "fp64", "achieved": alg_tflops, "peak": peak_tflops, "unit": "TFLOP/s", "frac": alg_tflops / peak_tflops,
                 "traffic": profiled_dram_traffic(args.math),
                 "traffic_note": "DRAM bytes (read + write) of ONE launch of this kernel on 1.5e7 rays from the committed ncu --set full "
-                                "capture (profiles/r1c_emis_rk4_*.txt): the kernel has no input or output arrays, the few MB are "
-                                "register spills evicted from L2; algorithmic HBM traffic is the 4 KB histogram",
+                                "capture (profiles/r2_emis_rk4_*.txt): the kernel has no input or output arrays, the few MB are "
+                                "local-memory lines evicted from L2; algorithmic HBM traffic is the 4 KB histogram",
                 "how": f"achieved = {FLOP_PER_RK4_STEP:.0f} algorithmic FP64 flop per RK4 step (SURVEY 8d) x {steps_per_step // world} steps "
                        f"per launch / {kernel_ms:.1f} ms (CUDA events around the fused kernel, mean over timed steps, max over ranks); "
                        "peak = DFMA micro-benchmark kt_fp64_peak() measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
-                       "HBM traffic of the kernel is ~0 (rays never leave the SM), see profiles/ for the ncu-counted FP64 pipe view",
+                       "HBM traffic of the kernel is ~0 (rays never leave the SM), see profiles/ for the ncu-counted FP64 pipe view. "
+                       "The binding resource is the SMSP dispatch port: an FP64 instruction holds it for two cycles, anything else "
+                       "for one, and the measured cycles per warp-step equal 2 x (FP64 instructions) + (other instructions) to 1 % "
+                       "(DESIGN.md section 4), so frac is capped by the instruction mix of an IEEE division (6 FP64 + 5 other) "
+                       "and root (8 + 4), not by the DFMA rate",
                 "kernel_ms": kernel_ms,
                 "hbm": hbm_view(profiled_dram_traffic(args.math)),
             },

@@ -70,4 +70,16 @@ with open(out, "w") as f:
             f.write(f"{op:10s} {100 * n / tot:6.2f} % {per}   samples {100 * samp[op] / stot:5.2f} %\n")
         if ray_steps:
             f.write(f"TOTAL      {tot / ray_steps:.1f} thread instructions per ray-step\n")
+            # the issue model: an FP64 instruction holds the SMSP's dispatch port for two cycles, anything else
+            # for one -> cycles per warp-step and SMSP = 2 F + O, to be compared with the measured active cycles
+            F = sum(by[k] for k in ("DFMA", "DMUL", "DADD", "DSETP")) / ray_steps
+            O = tot / ray_steps - F
+            try:
+                n_smsp = 4 * 148
+                measured = float(g("sm__cycles_active.avg")) / (ray_steps / 32.0 / n_smsp)
+                f.write(f"\n# issue model: F = {F:.1f} FP64-pipe instructions (incl. DSETP), O = {O:.1f} others per ray-step\n"
+                        f"issue_model_cycles_per_warp_step = 2 F + O = {2 * F + O:.0f}\n"
+                        f"measured_cycles_per_warp_step_per_SMSP = {measured:.0f}   (sm__cycles_active / (ray-steps / 32 / 592 SMSPs))\n")
+            except Exception as e:  # noqa: BLE001
+                f.write(f"# issue model unavailable: {e}\n")
 print("wrote", out)
