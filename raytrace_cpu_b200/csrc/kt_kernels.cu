@@ -737,9 +737,20 @@ __global__ void k_selftest_lean(unsigned long long* out, unsigned long long seed
         const double th = 0.05 + 3.0 * u01();
         LeanVals v;
         lean_rhs<true>(P, s, r, th, v);
-        const Mom m = momenta(P, s.k, s.h, s.Q, s.ka, 1, 1, r, th);
+        // the reference's expressions (kerr.h:308-334) with the library's sincos, / and sqrt
         double sn, cs;
         sincos(th, &sn, &cs);
+        Mom m;
+        {
+            const double sn2 = sn * sn, rr = r * r, ac = a * cs;
+            const double rho2 = rr + ac * ac, del = rr - 2 * r + a * a, rho2del = rho2 * del;
+            m.pt = ((rho2 * (rr + a * a) + 2 * a * a * r * sn2) * s.k - 2 * a * r * s.h) / rho2del;
+            m.pph = (2 * a * r * sn2 * s.k + (rho2 - 2 * r) * s.h) / (sn2 * rho2del);
+            const double thsq = (s.Q + (s.k * a * cs + s.h * cs / sn) * (s.k * a * cs - s.h * cs / sn)) / (rho2 * rho2);
+            m.pth = sqrt(fabs(thsq));
+            const double rsq = (s.k * m.pt - s.h * m.pph - rho2 * m.pth * m.pth) * del / rho2;
+            m.pr = sqrt(fabs(rsq));
+        }
         const double got[6] = {v.pt, v.pph, v.pth_abs, v.pr_abs, v.s2, 1.0 - v.s2};
         const double want[6] = {m.pt, m.pph, m.pth, m.pr, sn * sn, cs * cs};
         for (int j = 0; j < 6; j++) {
