@@ -21,6 +21,7 @@ ap.add_argument("--integrator", default="rk4", choices=["rk4", "rk45"])
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--min-blocks", type=int, default=0)
 ap.add_argument("--h", type=float, default=10.0)
+ap.add_argument("--rayset", action="store_true", help="profile the ray-set kernel (144-B records in HBM, results written back) instead")
 args = ap.parse_args()
 
 ctx = K.get_context(0)
@@ -33,6 +34,23 @@ src = K.pointsource_desc([0.0, args.h, 1e-3, 1.5707], 0.0, dcos, dbeta, bench.CO
 bins = K.emissivity_bins(bench.SPIN, Nr=100, src=src)
 mode = A.MATH_FAST if args.math == "fast" else A.MATH_EXACT
 meth = K.Integrator.RK45 if args.integrator == "rk45" else K.Integrator.RK4
+if args.rayset:
+    import ctypes as C
+    import math
+    ps = K.PointSource([0.0, args.h, 1e-3, 1.5707], 0.0, bench.SPIN, A.TOL, dcos, dbeta, bench.COS0, bench.COSMAX, bench.BETA0, bench.BETAMAX,
+                       ctx=ctx, math_mode=mode)
+    ps.redshift_start()
+    tr = K.api.make_tracer(bench.SPIN, A.TOL)
+    stop = K.api.thetalim_stop(math.pi / 2)
+    run = K.api.make_run(meth, 1000.0, -1, mode)
+    t0 = time.perf_counter()
+    K.lib.check(ctx.L.kt_rayset_trace(ps._rs, C.byref(tr), C.byref(stop), C.byref(run)))
+    ctx.synchronize() if hasattr(ctx, "synchronize") else K.lib.check(ctx.L.kt_synchronize(ctx.h))
+    dt = time.perf_counter() - t0
+    n = ps.get_count()
+    print(f"ray-set kernel: {n} slots, {dt * 1e3:.1f} ms, {n / dt:.3e} rays/s; algorithmic HBM traffic {n * (128 + 88) / 1e9:.2f} GB "
+          f"-> {n * (128 + 88) / dt / 1e9:.1f} GB/s", flush=True)
+    sys.exit(0)
 for i in range(args.reps):
     t0 = time.perf_counter()
     out = K.emissivity(src, bench.SPIN, bins, method=meth, ctx=ctx, math_mode=mode)
