@@ -821,7 +821,9 @@ extern "C" int kt_trace(kt_ctx* c, const kt_tracer* tr, const kt_stop* stop, con
     if (c->zerocopy) {
         cudaPointerAttributes pa;
         memset(&pa, 0, sizeof(pa));
-        if (cudaPointerGetAttributes(&pa, rays) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
+        // (the kernel moves records with 128-bit accesses: a host array that is not 16-byte aligned goes through the staged copy)
+        if (cudaPointerGetAttributes(&pa, rays) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer &&
+            (reinterpret_cast<uintptr_t>(pa.devicePointer) & 15u) == 0) {
             TraceParams P = P0;
             if (int rc = set_work(P, c, n, nullptr)) return rc;
             if (int rc = ensure_scratch(c, KT_NCOUNTERS * sizeof(double))) return rc;

@@ -1,5 +1,6 @@
 // kt_kernels.cu -- IO policies, kernel instantiations and launchers.  Compiled once per arithmetic mode
 // (Makefile: -DKT_FAST=0 -fmad=false  ->  kt_kernels_exact.o ;  -DKT_FAST=1 -fmad=true  ->  kt_kernels_fast.o).
+#include <cstddef>
 #include <type_traits>
 
 #include "kt_kernels.h"
@@ -33,17 +34,25 @@ struct RaysetIO {
     __device__ double* counters_out() { return counters; }
 
     // run_raytrace skips rays with steps < 0 or steps >= steplim: raytracer.cpp:116-117
+    // The 144-byte record as nine 16-byte words: w[0] = {t, r}, w[1] = {theta, phi}, w[2] = {pt, pr}, w[3] = {ptheta, pphi},
+    // w[4] = {k, h}, w[5] = {Q, emit}, w[6] = {redshift, steps | status}, w[7] = {rdot_sign | thetadot_sign, rdot_flips |
+    // equatorial_crossings}, w[8] = {alpha, beta}.  Records are read and written with 128-bit accesses (LDG.128 / STG.128):
+    // consecutive lanes of a refill take consecutive records, so a warp's loads cover one contiguous 4.6-KB span -- in HBM, or
+    // over PCIe when `rays` is the application's pinned host array.
     __device__ bool make(const TraceParams& P, long long idx, RayIn& in, LaneCounters&)
     {
-        const kt_ray& q = rays[idx];
-        const int st = q.steps;
+        static_assert(sizeof(kt_ray) == 144 && offsetof(kt_ray, steps) == 104 && offsetof(kt_ray, rdot_sign) == 112, "kt_ray layout");
+        const double2* w = reinterpret_cast<const double2*>(rays + idx);
+        const double2 w6 = w[6];
+        const int st = __double2loint(w6.y), status = __double2hiint(w6.y);
         if (st < 0 || st >= P.steplim) return false;
-        in.t = q.t; in.r = q.r; in.th = q.theta; in.ph = q.phi;
-        in.k = q.k; in.h = q.h; in.Q = q.Q;
-        in.pt = q.pt; in.pr = q.pr; in.pth = q.ptheta; in.pph = q.pphi;
+        const double2 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4], w5 = w[5], w7 = w[7];
+        in.t = w0.x; in.r = w0.y; in.th = w1.x; in.ph = w1.y;
+        in.pt = w2.x; in.pr = w2.y; in.pth = w3.x; in.pph = w3.y;
+        in.k = w4.x; in.h = w4.y; in.Q = w5.x;
         in.emit = 0; in.step0 = 0;
-        in.steps0 = st; in.status0 = q.status;
-        in.sr = q.rdot_sign; in.sth = q.thetadot_sign; in.flips = q.rdot_flips; in.cross = q.equatorial_crossings;
+        in.steps0 = st; in.status0 = status;
+        in.sr = __double2loint(w7.x); in.sth = __double2hiint(w7.x); in.flips = __double2loint(w7.y); in.cross = __double2hiint(w7.y);
         return true;
     }
     __device__ void pack_in(Stage<ND_IN, NI_IN>& b, int slot, const RayIn& in)
@@ -71,15 +80,17 @@ struct RaysetIO {
     // write-back: raytracer.cpp:952-967
     __device__ void retire(const TraceParams&, const RayOut& o, LaneCounters& c)
     {
-        kt_ray& q = rays[o.idx];
-        q.t = o.t; q.r = o.r; q.theta = o.th; q.phi = o.ph;
-        q.pt = o.pt; q.pr = o.pr; q.ptheta = o.pth; q.pphi = o.pph;
-        q.rdot_sign = o.sr; q.thetadot_sign = o.sth; q.rdot_flips = o.flips; q.equatorial_crossings = o.cross;
-        q.status = o.status;
         int st = o.steps0;
         if (o.steps > 0) st += o.steps;
         if (o.status & KT_STATUS_STEPLIM) st = -st;
-        q.steps = st;
+        double2* w = reinterpret_cast<double2*>(rays + o.idx);
+        w[0] = make_double2(o.t, o.r);
+        w[1] = make_double2(o.th, o.ph);
+        w[2] = make_double2(o.pt, o.pr);
+        w[3] = make_double2(o.pth, o.pph);
+        // (k, h, Q, emit, redshift, alpha, beta are not the trace's to write: w[4], w[5], w[8] and the first half of w[6] stay)
+        reinterpret_cast<double*>(w + 6)[1] = __hiloint2double(o.status, st);                       // steps | status
+        w[7] = make_double2(__hiloint2double(o.sth, o.sr), __hiloint2double(o.cross, o.flips));     // signs, flips | crossings
         count_terminal(c, o.steps, o.status);
     }
 };
