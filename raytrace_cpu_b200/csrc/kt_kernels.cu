@@ -22,6 +22,7 @@ struct RaysetIO {
     static constexpr bool PATHS = false;
     static constexpr bool NEED_PHI = true;
     static constexpr bool NEED_INFO = true;    // status bits, rdot_flips and equatorial_crossings are written back
+    static constexpr bool NEED_FAILED = true;  // ... and so are t and phi of a ray that failed on the step limit
     template <class H> __device__ void setup_paths(H&) {}
     __device__ long long path_first(long long) { return 0; }
     __device__ void path_done(long long, int) {}
@@ -141,6 +142,7 @@ struct EmisIOT {
     // the histogram reads r, theta, t, the redshift and the terminal class of a ray: its ERGO / NEG_ENERGY bits, radial turning
     // points and equatorial crossings are unobservable (emissivity.cpp:96-126), so the RK4 step does not evaluate them
     static constexpr bool NEED_INFO = false;
+    static constexpr bool NEED_FAILED = false;   // a ray with steps <= 0 is discarded before anything of it is read
     template <class H> __device__ void setup_paths(H&) {}
     __device__ long long path_first(long long) { return 0; }
     __device__ void path_done(long long, int) {}
@@ -263,6 +265,7 @@ struct PlaneIO {
     // image maps (imageplane_disc_image.cpp:122-161) read r, phi, t, the redshift and status & DEST; the compact per-ray
     // results of the caustic path carry status, rdot_flips and equatorial_crossings to the host
     static constexpr bool NEED_INFO = !IMAGE;
+    static constexpr bool NEED_FAILED = !IMAGE;
     template <class H> __device__ void setup_paths(H&) {}
     __device__ long long path_first(long long) { return 0; }
     __device__ void path_done(long long, int) {}
