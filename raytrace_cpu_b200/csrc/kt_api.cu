@@ -377,6 +377,7 @@ static int make_params(TraceParams& P, const kt_tracer* tr, const kt_stop* stop,
         P.steplim = run->steplim > 0 ? run->steplim : (run->integrator == KT_RK45 ? KT_RK45_STEPLIM : KT_STEPLIM); // raytracer.cpp:80
     }
     if (stop && (stop->kind < KT_STOP_THETALIM || stop->kind > KT_STOP_FLATPLANE)) return fail(KT_ERR_INVALID, "unknown stop kind %d", stop->kind);
+    P.stop._pad = 1 << P.stop.kind;    // one-hot copy of the kind for the device's bit tests (kt_device.cuh: dest_reached)
     const double a = tr->spin;
     if (run && (run->flags & KT_RUN_RETIRE_STUCK) && run->integrator == KT_RK45) {
         // innermost (prograde) circular photon orbit of |a|: no radial turning point exists below it
