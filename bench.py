@@ -346,6 +346,8 @@ def main():
         ocnt = A.EmisResult.from_packed(NR, hist.cpu().numpy()).counters
         other = {"math": oname, "value": int(ocnt[A.CNT_TRACED]) * args.steps / (oms.item() * 1e-3), "unit": "rays/s",
                  "ms_per_step": oms.item() / args.steps, "warmup": 1,
+                 # same accounting as `roofline`: 259 algorithmic flop per RK4 step of the reference's expressions, per GPU
+                 "roofline_frac": FLOP_PER_RK4_STEP * (int(ocnt[A.CNT_STEPS]) / world) / (oms.item() / args.steps * 1e-3) / 1e12 / peak_tflops,
                  "note": "same workload and timing rules; 'fast' = the reference's right-hand side evaluated through algebraically "
                          "equivalent, cheaper expressions with FMA contraction (kt_trace.cuh: rk4_step_lean); same step schedule; "
                          "per-ray deviations are in the class of the reference's own -march=native build (0.26 % of rays beyond "
