@@ -63,6 +63,35 @@ struct RaysetIO {
         staged = st + 9 * lane;
     }
 
+    // Coalesced stores of results.  A finished lane deposits the words the trace owns -- w[0..3] = t .. pphi and the 24 bytes
+    // steps | status, signs, flips | crossings -- with its record index in the warp's staging area (free between refills: 96 of a
+    // slot's 144 bytes); flush_one() then writes one ray's record with seven lanes: four 16-byte words (one 64-byte request)
+    // and three 8-byte words (one 24-byte request).  k, h, Q, emit, redshift, alpha, beta are not the trace's to write.
+    __device__ void deposit(const RayOut& o, LaneCounters& c)
+    {
+        int st = o.steps0;
+        if (o.steps > 0) st += o.steps;
+        if (o.status & KT_STATUS_STEPLIM) st = -st;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        double2* slot = reinterpret_cast<double2*>(smem + warp * RECORD_STAGE_BYTES + lane * 96);
+        slot[0] = make_double2(o.t, o.r);
+        slot[1] = make_double2(o.th, o.ph);
+        slot[2] = make_double2(o.pt, o.pr);
+        slot[3] = make_double2(o.pth, o.pph);
+        slot[4] = make_double2(__hiloint2double(o.status, st), __hiloint2double(o.sth, o.sr));
+        slot[5] = make_double2(__hiloint2double(o.cross, o.flips), __longlong_as_double(o.idx));
+        count_terminal(c, o.steps, o.status);
+    }
+    __device__ void flush_one(int src)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const unsigned char* slot = smem + warp * RECORD_STAGE_BYTES + src * 96;
+        const long long idx = *reinterpret_cast<const long long*>(slot + 88);
+        unsigned char* rec = reinterpret_cast<unsigned char*>(rays + idx);
+        if (lane < 4) reinterpret_cast<double2*>(rec)[lane] = reinterpret_cast<const double2*>(slot)[lane];
+        else if (lane < 7) reinterpret_cast<double*>(rec + 104)[lane - 4] = reinterpret_cast<const double*>(slot + 64)[lane - 4];
+    }
+
     // run_raytrace skips rays with steps < 0 or steps >= steplim: raytracer.cpp:116-117
     // The 144-byte record as nine 16-byte words: w[0] = {t, r}, w[1] = {theta, phi}, w[2] = {pt, pr}, w[3] = {ptheta, pphi},
     // w[4] = {k, h}, w[5] = {Q, emit}, w[6] = {redshift, steps | status}, w[7] = {rdot_sign | thetadot_sign, rdot_flips |
@@ -174,6 +203,8 @@ struct EmisIOT {
     static constexpr bool NEED_FAILED = false;   // a ray with steps <= 0 is discarded before anything of it is read
     static constexpr bool COOP_RECORDS = false;
     __device__ void stage(const TraceParams&, long long) {}
+    __device__ void deposit(const RayOut&, LaneCounters&) {}
+    __device__ void flush_one(int) {}
     template <class H> __device__ void setup_paths(H&) {}
     __device__ long long path_first(long long) { return 0; }
     __device__ void path_done(long long, int) {}
@@ -299,6 +330,8 @@ struct PlaneIO {
     static constexpr bool NEED_FAILED = !IMAGE;
     static constexpr bool COOP_RECORDS = false;
     __device__ void stage(const TraceParams&, long long) {}
+    __device__ void deposit(const RayOut&, LaneCounters&) {}
+    __device__ void flush_one(int) {}
     template <class H> __device__ void setup_paths(H&) {}
     __device__ long long path_first(long long) { return 0; }
     __device__ void path_done(long long, int) {}
