@@ -380,7 +380,11 @@ def main():
                 times.append(te)
         tt = torch.tensor([sum(times)], dtype=torch.float64, device=dev)
         nn = torch.tensor([float(n_e)], dtype=torch.float64, device=dev)
+        by_rank = [1e3 * sum(times) / args.steps]
         if world > 1:
+            gathered = [torch.zeros_like(tt) for _ in range(world)]
+            dist.all_gather(gathered, tt)
+            by_rank = [1e3 * g.item() / args.steps for g in gathered]
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dist.all_reduce(nn)
         rays_e = work.numpy().view(A.RAY_DTYPE)
@@ -400,7 +404,8 @@ def main():
                "transfer": ("zero-copy: the persistent kernel reads each ray's record from the pinned host array over PCIe when a lane "
                             "picks the ray up and writes the result record back when it retires (no staging copy)") if zero_copy
                            else "staged: cudaMemcpyAsync H2D -> kernel -> cudaMemcpyAsync D2H",
-               "rays_per_step_per_gpu": int(n_e), "ms_per_step": 1e3 * tt.item() / args.steps}
+               "rays_per_step_per_gpu": int(n_e), "ms_per_step": 1e3 * tt.item() / args.steps,
+               "ms_per_step_by_rank": [round(x, 1) for x in by_rank]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
