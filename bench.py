@@ -392,17 +392,18 @@ def main():
         frac_live = traced_e / max(n_e, 1)
         zero_copy = os.environ.get("KT_ZEROCOPY", "1") != "0"
         if zero_copy:
-            # the kernel reads the 32-byte sectors holding t..Q and steps..equatorial_crossings of every live record (128 of its
-            # 144 bytes; an unused slot costs the one sector with `steps`) and writes back t..pphi + the six ints (88 bytes)
-            h2d = traced_e * 128 + (n_e - traced_e) * 32
+            # the kernel reads every record whole (a warp copies the 32 consecutive 144-byte records of a refill as one coalesced
+            # span) and writes back t..pphi + the six ints of every traced ray (88 bytes)
+            h2d = n_e * 144
             d2h = traced_e * 88
         else:
             h2d = d2h = n_e * 144
         e2e = {"value": nn.item() * frac_live * args.steps / tt.item(), "unit": "rays/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "call": "kt_trace(ctx, tracer, stop, run, Ray<double>* host_rays, n)  == Raytracer<double>::run_raytrace on rays[]",
-               "transfer": ("zero-copy: the persistent kernel reads each ray's record from the pinned host array over PCIe when a lane "
-                            "picks the ray up and writes the result record back when it retires (no staging copy)") if zero_copy
+               "transfer": ("zero-copy: the persistent kernel reads the records from the pinned host array over PCIe when a warp refills "
+                            "(32 consecutive records per coalesced load) and writes a ray's results back when it retires "
+                            "(no staging copy)") if zero_copy
                            else "staged: cudaMemcpyAsync H2D -> kernel -> cudaMemcpyAsync D2H",
                "rays_per_step_per_gpu": int(n_e), "ms_per_step": 1e3 * tt.item() / args.steps,
                "ms_per_step_by_rank": [round(x, 1) for x in by_rank]}

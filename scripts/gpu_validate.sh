@@ -21,3 +21,6 @@ cap() { # name minb math
 cap r2_exact 0 exact
 cap r2_fast 0 fast
 du -sh gpurun_out; tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/selftest.log; cat gpurun_out/bench.json
+# the ray-set kernel (HBM-resident records: the write-back traffic)
+timeout 600 ncu --set full --clock-control none -k regex:trace_persistent -c 1 -f -o /tmp/r2_rayset python scripts/gpu_profile.py --rays 1.6e7 --rayset > gpurun_out/ncu_r2_rayset.log 2>&1
+cp /tmp/r2_rayset.ncu-rep gpurun_out/ 2>/dev/null
