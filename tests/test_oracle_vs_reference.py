@@ -247,6 +247,55 @@ def test_live_reference_negative_and_zero_thetalim(orc, tl, integ):
     assert_bit_identical(rays, h.rays(), skip=("redshift",))
 
 
+SPIN_SWEEP = (0.0, 0.5, -0.9, 1.0)     # Schwarzschild, moderate, retrograde, extremal (horizon = isco = 1, Delta has a double root)
+
+
+def spin_sweep_setup(orc, spin, stopk):
+    """An off-axis source (h != 0 for every ray) at r = 6, theta = 0.7 above a disc with the spin's own ISCO."""
+    src = ob.make_pointsource([0, 6, 0.7, 0.3], 0.1, 0.1, cosalpha0=-0.995, cosalphamax=0.995, beta0=-np.pi, betamax=np.pi)
+    stop = ob.make_stop(stopk, r_isco=orc.kerr_isco(spin, +1), r_out=50.0)
+    return src, stop
+
+
+def oracle_spin_sweep(orc, spin, integ, stopk):
+    src, stop = spin_sweep_setup(orc, spin, stopk)
+    tr = orc.tracer(spin, A.TOL)
+    rays = orc.pointsource_rays(tr, src)
+    orc.redshift_start(rays, tr, 0.0)
+    orc.trace(rays, tr, stop, ob.make_run(integ, r_max=200.0, steplim=20000))
+    orc.range_phi(rays)
+    if stopk == A.STOP_THETALIM:
+        orc.redshift(rays, tr, -1.0)
+    else:
+        orc.redshift_dest(rays, tr, stop)
+    return rays
+
+
+@needs_ref
+@pytest.mark.parametrize("integ", [A.RK4, A.RK45])
+@pytest.mark.parametrize("stopk", [A.STOP_THETALIM, A.STOP_ISCODISC])
+@pytest.mark.parametrize("spin", SPIN_SWEEP)
+def test_live_reference_spin_sweep(orc, spin, stopk, integ):
+    """Every other fixture is a = +-0.998; the restatement must follow the reference at any spin, a = 0 and |a| = 1 included."""
+    ref = ob.Ref()
+    src, stop = spin_sweep_setup(orc, spin, stopk)
+    h = ref.pointsource(src, spin)
+    assert ref.kerr_isco(spin, +1) == orc.kerr_isco(spin, +1) and ref.kerr_horizon(spin) == orc.kerr_horizon(spin)
+    h.redshift_start()
+    h.run(stop, ob.make_run(integ, r_max=200.0, steplim=20000))
+    h.range_phi()
+    if stopk == A.STOP_THETALIM:
+        h.redshift(-1.0)
+    else:
+        h.redshift_dest(stop)
+    rays = oracle_spin_sweep(orc, spin, integ, stopk)
+    assert len(rays) == h.count() == 1334
+    assert_bit_identical(rays, h.rays())
+    st = rays["status"][rays["steps"] != -1]
+    # the grid exercises every ending: the disc / theta limit, escape, and capture (RK45 stalls there until the step limit)
+    assert (st & A.STATUS_DEST).any() and (st & A.STATUS_RLIM).any() and (st & (A.STATUS_HORIZON | A.STATUS_STEPLIM)).any()
+
+
 @needs_ref
 @pytest.mark.parametrize("bundles", [False, True])
 def test_live_reference_image_plane(orc, bundles):
