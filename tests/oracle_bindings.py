@@ -204,6 +204,12 @@ class RefSource:
     def set_rk45_tol(self, tol):
         self.L.ref_set_rk45_tol(self.h, tol)
 
+    def set_max_tstep(self, max_, rlim):
+        self.L.ref_set_max_tstep(self.h, max_, rlim)
+
+    def set_max_phistep(self, max_):
+        self.L.ref_set_max_phistep(self.h, max_)
+
     def redshift_start(self):
         self.L.ref_source_redshift_start(self.h)
 

@@ -296,6 +296,44 @@ def test_live_reference_spin_sweep(orc, spin, stopk, integ):
     assert (st & A.STATUS_DEST).any() and (st & A.STATUS_RLIM).any() and (st & (A.STATUS_HORIZON | A.STATUS_STEPLIM)).any()
 
 
+# set_max_tstep(max, rlim) / set_max_phistep(max) (raytracer.h:187-196): tighter caps, a cap radius inside the grid, and both
+# "off" spellings (0 and negative: the propagators test `> 0`, raytracer.cpp:861-866)
+STEP_CAPS = {"tight": (0.25, 50.0, 0.02), "t_off": (0.0, 100.0, 0.1), "phi_off": (1.0, 100.0, -1.0), "both_off": (-1.0, 0.0, 0.0),
+             "wide_rlim": (0.5, 1e4, 0.1)}
+
+
+def oracle_step_caps(orc, caps, integ):
+    src = ob.make_pointsource([0, 5, 1e-3, 0], 0.1, 0.1, cosalpha0=-0.995, cosalphamax=0.995, beta0=-np.pi, betamax=np.pi)
+    tr = orc.tracer(SPIN, A.TOL)
+    tr.max_tstep, tr.maxtstep_rlim, tr.max_phistep = STEP_CAPS[caps] if isinstance(caps, str) else caps
+    rays = orc.pointsource_rays(tr, src)
+    orc.redshift_start(rays, tr, 0.0)
+    orc.trace(rays, tr, ob.make_stop(), ob.make_run(integ, r_max=300.0, steplim=50000))
+    orc.range_phi(rays)
+    orc.redshift(rays, tr, -1.0)
+    return src, rays
+
+
+@needs_ref
+@pytest.mark.parametrize("integ", [A.RK4, A.RK45])
+@pytest.mark.parametrize("caps", sorted(STEP_CAPS))
+def test_live_reference_step_caps(orc, caps, integ):
+    ref = ob.Ref()
+    src, rays = oracle_step_caps(orc, caps, integ)
+    h = ref.pointsource(src, SPIN)
+    mt, rl, mp = STEP_CAPS[caps]
+    h.set_max_tstep(mt, rl)
+    h.set_max_phistep(mp)
+    h.redshift_start()
+    h.run(ob.make_stop(), ob.make_run(integ, r_max=300.0, steplim=50000))
+    h.range_phi()
+    h.redshift(-1.0)
+    assert_bit_identical(rays, h.rays())
+    if integ == A.RK4 and caps != "t_off":   # the caps change the step schedule (the default t cap alone never binds on this grid)
+        _, base = oracle_step_caps(orc, (A.MAXDT, A.MAXDT_RLIM, A.MAXDPHI), integ)
+        assert (base["steps"] != rays["steps"]).any()
+
+
 @needs_ref
 @pytest.mark.parametrize("bundles", [False, True])
 def test_live_reference_image_plane(orc, bundles):
