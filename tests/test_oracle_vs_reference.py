@@ -361,6 +361,60 @@ def test_live_reference_image_plane(orc, bundles):
         assert np.isnan(rays["r"]).sum() == 1     # the exact-centre pixel (b = 0 -> asin(0/0)), SURVEY 8c
 
 
+# image-plane geometries beyond the fixtures' (30 / 60 degrees, square grids, phi0 = 0): near face-on, near edge-on, a rotated
+# observer, rectangular grids with dx != dy (the x coordinate steps by dy, imageplane.cpp:45), other spins
+PLANE_SWEEP = {
+    "faceon":   dict(spin=0.998, dist=800.0, incl=3.0, x0=-12.0, xmax=12.0, nx=21, ny=21, phi0=0.0),
+    "edgeon":   dict(spin=0.998, dist=800.0, incl=87.0, x0=-12.0, xmax=12.0, nx=21, ny=21, phi0=0.0),
+    "rotated":  dict(spin=0.5, dist=600.0, incl=45.0, x0=-10.0, xmax=10.0, nx=19, ny=19, phi0=0.7),
+    "rect":     dict(spin=0.9, dist=600.0, incl=70.0, x0=-15.0, xmax=15.0, nx=30, ny=12, y0=-6.0, ymax=9.0, phi0=-2.0),
+    "schwarz":  dict(spin=0.0, dist=600.0, incl=50.0, x0=-10.0, xmax=10.0, nx=19, ny=19, phi0=0.0),
+    "retro":    dict(spin=-0.7, dist=600.0, incl=50.0, x0=-10.0, xmax=10.0, nx=19, ny=19, phi0=0.0),
+}
+
+
+def plane_sweep_setup(orc, name):
+    c = PLANE_SWEEP[name]
+    ip = ob.make_imageplane(c["dist"], c["incl"], c["x0"], c["xmax"], c["nx"], y0=c.get("y0"), ymax=c.get("ymax"), ny=c["ny"],
+                            phi0=c["phi0"])
+    # the tracer of an image plane stores the negated spin (imageplane.cpp:12); the disc's ISCO is that of the hole's own spin
+    # a disc smaller than the field of view: the rays outside r_out cross the plane and go on to the horizon or to r_max
+    stop = ob.make_stop(A.STOP_ISCODISC, r_isco=orc.kerr_isco(c["spin"], +1), r_out=8.0)
+    return c, ip, stop
+
+
+def oracle_plane_sweep(orc, name, integ):
+    c, ip, stop = plane_sweep_setup(orc, name)
+    tr = orc.tracer(-c["spin"], A.PRECISION)
+    rays = orc.imageplane_rays(tr, ip)
+    orc.redshift_start(rays, tr, 0.0, True)
+    orc.trace(rays, tr, stop, ob.make_run(integ, r_max=1.1 * c["dist"], steplim=20000))
+    orc.redshift_dest(rays, tr, stop, True)
+    orc.range_phi(rays)
+    return rays
+
+
+@needs_ref
+@pytest.mark.parametrize("integ", [A.RK4, A.RK45])
+@pytest.mark.parametrize("name", sorted(PLANE_SWEEP))
+def test_live_reference_plane_sweep(orc, name, integ):
+    ref = ob.Ref()
+    c, ip, stop = plane_sweep_setup(orc, name)
+    h = ref.imageplane(ip, c["spin"])
+    rr = h.rays(copy=False)
+    rr["rdot_flips"][:] = 0            # uninitialised in the reference
+    rr["equatorial_crossings"][:] = 0
+    h.redshift_start()
+    h.run(stop, ob.make_run(integ, r_max=1.1 * c["dist"], steplim=20000))
+    h.redshift_dest(stop, True)
+    h.range_phi()
+    rays = oracle_plane_sweep(orc, name, integ)
+    assert len(rays) == h.count() == (c["nx"] + 1) * (c["ny"] + 1)
+    assert_bit_identical(rays, h.rays())
+    st = rays["status"][rays["steps"] != -1]
+    assert (st & A.STATUS_DEST).any() and (st & A.STATUS_RLIM).any()     # every geometry sees the disc and the sky behind it
+
+
 @needs_ref
 @pytest.mark.parametrize("integ", [A.EULER, A.RK4, A.RK45])
 def test_live_reference_ray_paths(orc, integ):
