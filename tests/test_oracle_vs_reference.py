@@ -272,8 +272,8 @@ def oracle_spin_sweep(orc, spin, integ, stopk):
 
 
 @needs_ref
-@pytest.mark.parametrize("integ", [A.RK4, A.RK45])
-@pytest.mark.parametrize("stopk", [A.STOP_THETALIM, A.STOP_ISCODISC])
+@pytest.mark.parametrize("integ,stopk", [(A.EULER, A.STOP_THETALIM), (A.RK4, A.STOP_THETALIM), (A.RK4, A.STOP_ISCODISC),
+                                         (A.RK45, A.STOP_THETALIM), (A.RK45, A.STOP_ISCODISC)])
 @pytest.mark.parametrize("spin", SPIN_SWEEP)
 def test_live_reference_spin_sweep(orc, spin, stopk, integ):
     """Every other fixture is a = +-0.998; the restatement must follow the reference at any spin, a = 0 and |a| = 1 included."""
