@@ -895,6 +895,19 @@ __global__ void k_selftest_divsqrt(unsigned long long* out, unsigned long long s
             if (sx > bad_s) bad_s = sx;
             continue;
         }
+        if (mode == 7) {            // kt_root5 against pow(x, 0.2) on [2^-40, 2^40]: out[0] = largest distance in ulps, out[1] = the step
+                                    // factor's special cases that came out wrong (0, tiny, huge, NaN)
+            const double x = __longlong_as_double((long long)((ua & 0x000fffffffffffffull) | ((unsigned long long)(1023 - 40 + (ub % 80)) << 52)));
+            const long long d = __double_as_longlong(kt_root5(x)) - __double_as_longlong(pow(x, 0.2));
+            const unsigned long long ad = (unsigned long long)(d < 0 ? -d : d);
+            if (ad > bad_d) bad_d = ad;
+            const double sp[6] = {0.0, 1e-300, 9.0e-13, 1e10, 1e300, __longlong_as_double(0x7ff8000000000000ll)};
+            const double want[6] = {0.1, 0.1, 0.1, 5.0, 5.0, 5.0};
+            if (rk45_step_factor(sp[i % 6]) != want[i % 6]) bad_s++;
+            const double f = rk45_step_factor(x), g = std_max(0.1, std_min(5.0, 0.9 * pow(x, 0.2)));
+            if (fabs(f - g) > 1e-15 * g) bad_s++;
+            continue;
+        }
         if (mode == 5) {            // ydiv / ysqrt / ydivc (range-propagated acceptance) over the whole domain their callers establish
             auto with_exp = [&](unsigned long long u, int lo, int hi) {
                 const unsigned long long e = (unsigned long long)(1023 + lo) + next() % (unsigned long long)(hi - lo + 1);
@@ -936,6 +949,7 @@ __global__ void k_selftest_divsqrt(unsigned long long* out, unsigned long long s
         else if (__double_as_longlong(s) != __double_as_longlong(sr) && !(s != s && sr != sr)) bad_s++;
     }
     if (mode == 6) { atomicMax(&out[0], bad_d); atomicMax(&out[1], bad_s); atomicAdd(&out[4], (unsigned long long)per_thread); return; }
+    if (mode == 7) { atomicMax(&out[0], bad_d); atomicAdd(&out[1], bad_s); atomicAdd(&out[4], (unsigned long long)per_thread); return; }
     atomicAdd(&out[0], bad_d); atomicAdd(&out[1], bad_s); atomicAdd(&out[2], rej_d); atomicAdd(&out[3], rej_s);
     atomicAdd(&out[4], (unsigned long long)per_thread);
 #endif
