@@ -150,7 +150,10 @@ extern "C" kt_ctx* kt_create(int device)
         return nullptr;
     }
     kt_ctx* c = new (std::nothrow) kt_ctx;
-    if (!c) return nullptr;
+    if (!c) {
+        fail(KT_ERR_NOMEM, "host allocation of the context failed");
+        return nullptr;
+    }
     c->device = device;
     cudaDeviceProp prop;
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
@@ -158,7 +161,7 @@ extern "C" kt_ctx* kt_create(int device)
         cudaMalloc(&c->d_queue, 2 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(c->d_queue, 0, 2 * sizeof(unsigned long long)) != cudaSuccess) {
         fail(KT_ERR_CUDA, "context creation failed: %s", cudaGetErrorString(cudaGetLastError()));
-        delete c;
+        kt_destroy(c);      // (frees whichever of the stream / queue already exists)
         return nullptr;
     }
     c->sm_count = prop.multiProcessorCount;
@@ -272,8 +275,6 @@ extern "C" void kt_host_free(void* p)
 {
     if (p) cudaFreeHost(p);
 }
-
-extern "C" int kt_aborted(kt_ctx* c);
 
 static LaunchCfg cfg_of(kt_ctx* c)
 {
@@ -1203,9 +1204,13 @@ extern "C" int kt_fp64_peak(kt_ctx* c, double* tflops)
     if (int rc = ctx_bind(c)) return rc;
     if (!tflops) return fail(KT_ERR_INVALID, "null output");
     const int blocks = c->sm_count * 4, threads = 256, iters = 1024;
-    cudaEvent_t e0, e1;
-    KT_CUDA(cudaEventCreate(&e0));
-    KT_CUDA(cudaEventCreate(&e1));
+    struct Events {      // destroyed on every return path
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } ev;
+    KT_CUDA(cudaEventCreate(&ev.a));
+    KT_CUDA(cudaEventCreate(&ev.b));
+    const cudaEvent_t e0 = ev.a, e1 = ev.b;
     const KernelTable* T = kt_kernel_table_fast();
     double best = 0;
     for (int rep = 0; rep < 4; rep++) {
@@ -1220,8 +1225,6 @@ extern "C" int kt_fp64_peak(kt_ctx* c, double* tflops)
         const double tf = 2.0 * fmas / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     *tflops = best;
     return KT_OK;
 }
